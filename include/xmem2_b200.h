@@ -1,0 +1,115 @@
+/* xmem2_b200.h — C ABI of the B200-native XMem++ hot path (libxmem2_b200.so).
+ *
+ * Every entry point takes plain device pointers + sizes and an explicit cudaStream_t (passed as
+ * void*), never allocates, never synchronises, and returns 0 on success or a negative code with
+ * the message available from xm_last_error().  No torch types cross this boundary.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo mbzuai-metaverse/XMem2):
+ *   xm_affinity_readout        model/memory_util.py:7-39 (get_similarity) + :41-65 (do_softmax, top-k)
+ *                              + inference/memory_manager.py:57-59,61-190 (_readout / match_memory)
+ *   xm_query_pack, xm_key_pack model/memory_util.py:22-26 (operand preparation of get_similarity)
+ *   xm_conv2d_nhwc             every nn.Conv2d(+BatchNorm2d+ReLU+residual) on the path:
+ *                              model/resnet.py:46-114, model/modules.py:22-41,178-211,229-250,
+ *                              model/group_modules.py:29-54
+ *   xm_* element-wise ops      model/modules.py:63-74,88-99,135-138,166-170,236-247, model/cbam.py:23-77,
+ *                              model/group_modules.py:15-26, model/aggregate.py:6-16
+ */
+#ifndef XMEM2_B200_H
+#define XMEM2_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XM_OK 0
+#define XM_ERR_ARG (-1)
+#define XM_ERR_CUDA (-2)
+#define XM_ERR_WORKSPACE (-3)
+
+#define XM_CK 64        /* key channels  (util/configuration.py:144) */
+#define XM_CV 512       /* value channels (util/configuration.py:158) */
+#define XM_MAX_GROUPS 8
+#define XM_MAX_TOPK 32
+
+const char* xm_last_error(void);
+int xm_version(void);
+/* diagnostics: {valid, tag, blockIdx.xyz, threadIdx.x, parity} of the last mbarrier-timeout trap */
+int xm_debug_last_trap(int* out7);
+
+/* ---------------------------------------------------------------- memory read (K1) */
+/* One memory bank (KeyValueMemoryStore, inference/kv_memory_store.py:4-239) as the kernel sees it. */
+typedef struct {
+    const void* keys;       /* fp16 [cap][128]: row n = (k[n,:]^2 , k[n,:])  — "packed" keys           */
+    const float* shrinkage; /* fp32 [cap]                                                              */
+    const void* values;     /* fp16 [n_obj_cap][512][cap]  (reference layout v[g] = [n_g, CV, N_g])    */
+    float* usage;           /* fp32 [cap] or NULL; += column sums of the group-0 affinity (memory_util.py:62-63) */
+    int64_t cap;            /* allocated columns (multiple of 8)                                       */
+    int32_t n_obj_cap;      /* allocated value planes                                                   */
+    int32_t size;           /* columns in use                                                           */
+} xm_bank_t;
+
+/* An object group reads a SUFFIX of each bank's columns (memory_manager.py:98-128,162-182). */
+typedef struct {
+    int32_t obj_begin;      /* first value plane (object index, 0-based, background excluded)          */
+    int32_t n_obj;          /* planes in this group                                                     */
+    int32_t begin[3];       /* first visible column per bank; the range is [begin, bank.size)          */
+} xm_group_t;
+
+typedef struct {
+    xm_bank_t banks[3];     /* concat order of the reference: long-term, working, permanent (memory_manager.py:82) */
+    int32_t n_groups;
+    xm_group_t groups[XM_MAX_GROUPS];
+    const void* qp;         /* fp16 [hw_pad][128] from xm_query_pack                                    */
+    const float* bsq;       /* fp32 [hw_pad]      from xm_query_pack                                    */
+    int32_t hw;             /* query positions (h*w)                                                    */
+    int32_t hw_pad;         /* hw rounded up to 128                                                     */
+    int32_t top_k;          /* <= XM_MAX_TOPK                                                           */
+    int32_t n_obj_total;
+    void* readout_chw;      /* fp16 [n_obj_total][512][hw]   or NULL (reference layout)                 */
+    void* readout_hwc;      /* fp16 [n_obj_total][hw][512]   or NULL (NHWC, feeds the decoder directly) */
+    void* workspace;        /* >= xm_affinity_workspace_bytes()                                         */
+    int64_t workspace_bytes;
+    float* debug_scores;    /* optional fp32 [N_group0][hw_pad] dump of the similarity (tests only)     */
+} xm_affinity_args_t;
+
+int64_t xm_affinity_workspace_bytes(int32_t hw, int32_t n_obj_total);
+int xm_affinity_readout(const xm_affinity_args_t* args, void* stream);
+
+/* key [hw][64] fp16 (NHWC), selection [hw][64] fp16 -> qp [hw_pad][128] = (-e, 2*k*e), bsq = sum_c e*k^2 */
+int xm_query_pack(const void* key_hwc, const void* sel_hwc, int32_t hw, int32_t hw_pad, void* qp, float* bsq, void* stream);
+/* key [n][64] fp16 -> rows [n][128] = (k^2, k) written at dst */
+int xm_key_pack(const void* key_hwc, int32_t n, void* dst_rows, void* stream);
+
+/* ---------------------------------------------------------------- convolution (K2-K4) */
+typedef struct {
+    const void* ptr;        /* fp16 NHWC [batch][H][W][C]                                               */
+    int32_t channels;       /* multiple of 64                                                           */
+    int32_t broadcast;      /* 1: one image shared by every batch entry (MainToGroupDistributor)        */
+} xm_conv_src_t;
+
+typedef struct {
+    xm_conv_src_t src[3];   /* channel-concatenated inputs (torch.cat(..., dim=channels) without the copy) */
+    int32_t n_src;
+    int32_t batch, H, W;    /* input spatial size                                                       */
+    int32_t ksize;          /* 1 or 3 (7x7 stems go through xm_im2col_stem)                             */
+    int32_t stride;         /* 1 or 2 (padding = ksize/2)                                               */
+    const void* weight;     /* fp16 [cout_pad][ksize*ksize][cin_total]   (BN folded)                    */
+    const float* bias;      /* fp32 [cout_pad]                                                          */
+    int32_t cout;           /* real output channels                                                     */
+    int32_t cout_pad;       /* multiple of 64                                                           */
+    const void* residual;   /* fp16 NHWC [batch|1][Ho][Wo][cout] or NULL, added before the activation   */
+    int32_t residual_broadcast;
+    int32_t relu;           /* apply ReLU to `out`                                                      */
+    void* out;              /* fp16 NHWC [batch][Ho][Wo][out_stride] or NULL                            */
+    void* out_relu;         /* optional second copy with ReLU applied (GroupResBlock needs g and relu(g)) */
+    int32_t out_stride;     /* channel stride of out/out_relu (>= cout)                                 */
+    int32_t out_offset;     /* first channel written                                                    */
+} xm_conv_args_t;
+
+int xm_conv2d_nhwc(const xm_conv_args_t* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,61 @@
+"""GPU parity of the fused similarity -> top-k softmax -> readout(+usage) kernel against the oracle math
+(reference: model/memory_util.py:7-65, inference/memory_manager.py:61-190).  Calls go through the C ABI."""
+import pytest
+import torch
+
+from tests import k1_ref
+
+pytestmark = pytest.mark.gpu
+
+# tolerance: P is rounded to fp16 (as the reference does under autocast, memory_manager.py:59) and the
+# readout is accumulated in fp32 then stored fp16 -> 2e-2 absolute on values ~N(0,1) sums.
+TOL_OUT = 2e-2
+TOL_SCORE = 2e-4
+TOL_USAGE = 2e-3
+
+
+def _check(case, top_k=30):
+    r = k1_ref.compare(case, top_k)
+    assert r['score_err'] < TOL_SCORE, r
+    assert r['layout_err'] == 0.0, r
+    assert r['out_err_clear'] < TOL_OUT, r
+    assert r['ambiguous'] <= max(3, case['hw'] // 50), r
+    assert r['usage_err'] < TOL_USAGE, r
+    assert abs(r['usage_sum'] - case['hw']) < 0.05 * case['hw'] + 1, r    # affinity columns sum to 1
+    return r
+
+
+def test_single_bank_small():
+    _check(k1_ref.make_case(hw=96, sizes=(0, 0, 700), n_obj=1, group_begins=[(0, 1, [0, 0, 0])], seed=1))
+
+
+def test_three_banks_ragged_sizes():
+    # sizes not multiples of the 64-column tile; hw not a multiple of 128
+    _check(k1_ref.make_case(hw=200, sizes=(130, 333, 517), n_obj=1, group_begins=[(0, 1, [0, 0, 0])], seed=2))
+
+
+def test_two_groups_suffix_ranges():
+    # group 1 (object 1) only sees a suffix of working/permanent memory and no long-term memory
+    case = k1_ref.make_case(hw=150, sizes=(128, 300, 405), n_obj=2,
+                            group_begins=[(0, 1, [0, 0, 0]), (1, 1, [128, 150, 135])], seed=3)
+    _check(case)
+
+
+def test_minimum_columns_equals_topk():
+    _check(k1_ref.make_case(hw=64, sizes=(0, 0, 30), n_obj=1, group_begins=[(0, 1, [0, 0, 0])], seed=4))
+
+
+def test_fewer_columns_than_topk_raises():
+    case = k1_ref.make_case(hw=64, sizes=(0, 0, 20), n_obj=1, group_begins=[(0, 1, [0, 0, 0])], seed=5)
+    with pytest.raises(RuntimeError, match='top_k'):
+        k1_ref.run_kernel(case)
+
+
+def test_two_objects_one_group():
+    _check(k1_ref.make_case(hw=128, sizes=(0, 256, 256), n_obj=2, group_begins=[(0, 2, [0, 0, 0])], seed=6))
+
+
+def test_config2_shape_480p():
+    # BASELINE.json config 2 at its largest memory: HW=1620, 5 permanent + 9 working frames, 1 object
+    case = k1_ref.make_case(hw=1620, sizes=(0, 9 * 1620, 5 * 1620), n_obj=1, group_begins=[(0, 1, [0, 0, 0])], seed=7)
+    _check(case)

@@ -1,0 +1,296 @@
+// conv_igemm.cu — implicit-GEMM convolution on tcgen05 for NHWC fp16 activations.
+//
+// One kernel serves every 1x1 / 3x3 (stride 1 or 2, padding k/2) convolution on the XMem++ path
+// (reference: nn.Conv2d call sites in model/resnet.py:46-114, model/modules.py:22-41,178-211,229-250,
+// model/group_modules.py:29-54), with BatchNorm folded into weight+bias on the host and bias /
+// residual-add / ReLU fused into the epilogue.
+//
+// GEMM view:  D[pixel, cout] = sum_{tap, cin} A[pixel + tap, cin] * W[cout, tap, cin]
+//   M tile = 128 output pixels arranged as a TW x TH rectangle (TW*TH = 128)
+//   N tile = BN output channels (64 or 128), K step = 64 input channels of one filter tap.
+//   A operand: ONE TMA box [64 ch, TW, TH, 1] of the NHWC input, shifted by the tap offset; TMA's
+//     out-of-bounds zero fill implements the convolution padding, and the box lands in shared memory
+//     as 128 rows (pixels) x 128 B with the 128-byte swizzle == the UMMA K-major SW128 layout.
+//     Stride-2 convs view the input as parity planes [C, 2, W/2, 2, H/2] (rank-5 map), which turns the
+//     strided gather into a plain box again.
+//   B operand: TMA box [64, BN] of the [cout_pad][taps*cin] weight matrix.
+//   Channel-concatenated inputs (torch.cat along C in the reference) are read from up to three source
+//   tensors without materialising the concat; a source may be broadcast over the batch.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
+#include "common.h"
+#include "tc5.cuh"
+
+using namespace tc5;
+
+namespace {
+
+constexpr int CONV_STAGES = 3;
+
+struct alignas(64) ConvMaps {
+    CUtensorMap a[3];
+    CUtensorMap w;
+};
+
+struct ConvP {
+    int n_src;
+    int cblocks[3];      // channels / 64 per source
+    int choff[3];        // channel offset of the source inside the concatenated input
+    int bcast[3];
+    int cin_total;
+    int ksize, stride, pad;
+    int tw, th, tiles_x, tiles_y;
+    int Ho, Wo, batch;
+    int cout;
+    int relu;
+    const float* bias;
+    const __half* residual;
+    int residual_bcast, residual_stride;
+    __half* out;
+    __half* out_relu;
+    int out_stride, out_offset;
+};
+
+template <int BN>
+struct ConvSmem {
+    alignas(1024) uint8_t a[CONV_STAGES][128 * 128];
+    alignas(1024) uint8_t b[CONV_STAGES][BN * 128];
+    alignas(8) uint64_t full[CONV_STAGES];
+    uint64_t empty[CONV_STAGES];
+    uint64_t done;
+    uint32_t tmem_base;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192)
+conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
+    extern __shared__ uint8_t smem_raw[];
+    ConvSmem<BN>& sm = *reinterpret_cast<ConvSmem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int tile = blockIdx.x;
+    const int tx_i = tile % p.tiles_x; tile /= p.tiles_x;
+    const int ty_i = tile % p.tiles_y; tile /= p.tiles_y;
+    const int b = tile;
+    const int x0 = tx_i * p.tw, y0 = ty_i * p.th;
+    const int n0 = blockIdx.y * BN;
+
+    const int taps = p.ksize * p.ksize;
+    int cb_total = 0;
+    for (int s = 0; s < p.n_src; ++s) cb_total += p.cblocks[s];
+    const int ksteps = taps * cb_total;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < CONV_STAGES; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+        mbar_init(&sm.done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) { tmem_alloc(&sm.tmem_base, BN); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int tap = 0; tap < taps; ++tap) {
+                const int kh = tap / p.ksize, kw = tap % p.ksize;
+                for (int s = 0; s < p.n_src; ++s) {
+                    const int bb = p.bcast[s] ? 0 : b;
+                    for (int cb = 0; cb < p.cblocks[s]; ++cb, ++it) {
+                        const int st = it % CONV_STAGES, ph = (it / CONV_STAGES) & 1;
+                        mbar_wait(&sm.empty[st], ph ^ 1, 21);
+                        mbar_expect_tx(&sm.full[st], 128 * 128 + BN * 128);
+                        if (p.stride == 1) {
+                            tma_load_4d(sm.a[st], &maps.a[s], &sm.full[st], cb * 64, x0 + kw - p.pad, y0 + kh - p.pad, bb);
+                        } else {
+                            // input pixel (2*yo + kh - pad, 2*xo + kw - pad) -> parity plane + half coordinate
+                            const int dy = kh - p.pad, dx = kw - p.pad;
+                            const int py = dy & 1, px = dx & 1;
+                            const int hy = (dy - py) / 2, hx = (dx - px) / 2;
+                            tma_load_5d(sm.a[st], &maps.a[s], &sm.full[st], cb * 64, px, x0 + hx, py, y0 + hy);
+                        }
+                        tma_load_2d(sm.b[st], &maps.w, &sm.full[st], tap * p.cin_total + p.choff[s] + cb * 64, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(128, BN);
+            for (int it = 0; it < ksteps; ++it) {
+                const int st = it % CONV_STAGES, ph = (it / CONV_STAGES) & 1;
+                mbar_wait(&sm.full[st], ph, 22);
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint64_t a = make_desc_sw128(smem_u32(sm.a[st]) + j * 32);
+                    uint64_t bd = make_desc_sw128(smem_u32(sm.b[st]) + j * 32);
+                    mma_f16_ss(tmem, a, bd, idesc, (it | j) ? 1u : 0u);
+                }
+                mma_commit(&sm.empty[st]);
+            }
+            mma_commit(&sm.done);
+        }
+    } else {
+        const int lane_base = (warp & 3) * 32;
+        const int row = lane_base + lane;
+        const int yo = y0 + row / p.tw, xo = x0 + row % p.tw;
+        const bool pix_ok = (yo < p.Ho) && (xo < p.Wo);
+        const size_t pix = ((size_t)b * p.Ho + yo) * p.Wo + xo;
+        const size_t rpix = ((size_t)(p.residual_bcast ? 0 : b) * p.Ho + yo) * p.Wo + xo;
+        mbar_wait(&sm.done, 0, 23);
+        tc_fence_after();
+        const bool vec_ok = (p.out_stride % 8 == 0) && (p.out_offset % 8 == 0) && (p.residual_stride % 8 == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(lane_base) << 16) + c0, r);
+            tmem_ld_wait();
+            const int n = n0 + c0;
+            if (!pix_ok || n >= p.cout) continue;
+            const bool full = (n + 32 <= p.cout) && vec_ok;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + ((n + j < p.cout) ? __ldg(p.bias + n + j) : 0.f);
+            if (p.residual) {
+                const __half* rp = p.residual + rpix * p.residual_stride + n;
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 u = *reinterpret_cast<const uint4*>(rp + j);
+                        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float2 f = __half22float2(h2[e]);
+                            v[j + 2 * e] += f.x; v[j + 2 * e + 1] += f.y;
+                        }
+                    }
+                } else {
+                    for (int j = 0; j < 32 && n + j < p.cout; ++j) v[j] += __half2float(rp[j]);
+                }
+            }
+            if (p.out) {
+                __half* op = p.out + pix * p.out_stride + p.out_offset + n;
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 u;
+                        u.x = pack_half2(p.relu ? fmaxf(v[j], 0.f) : v[j], p.relu ? fmaxf(v[j + 1], 0.f) : v[j + 1]);
+                        u.y = pack_half2(p.relu ? fmaxf(v[j + 2], 0.f) : v[j + 2], p.relu ? fmaxf(v[j + 3], 0.f) : v[j + 3]);
+                        u.z = pack_half2(p.relu ? fmaxf(v[j + 4], 0.f) : v[j + 4], p.relu ? fmaxf(v[j + 5], 0.f) : v[j + 5]);
+                        u.w = pack_half2(p.relu ? fmaxf(v[j + 6], 0.f) : v[j + 6], p.relu ? fmaxf(v[j + 7], 0.f) : v[j + 7]);
+                        *reinterpret_cast<uint4*>(op + j) = u;
+                    }
+                } else {
+                    for (int j = 0; j < 32 && n + j < p.cout; ++j) op[j] = __float2half_rn(p.relu ? fmaxf(v[j], 0.f) : v[j]);
+                }
+            }
+            if (p.out_relu) {
+                __half* op = p.out_relu + pix * p.out_stride + p.out_offset + n;
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 u;
+                        u.x = pack_half2(fmaxf(v[j], 0.f), fmaxf(v[j + 1], 0.f));
+                        u.y = pack_half2(fmaxf(v[j + 2], 0.f), fmaxf(v[j + 3], 0.f));
+                        u.z = pack_half2(fmaxf(v[j + 4], 0.f), fmaxf(v[j + 5], 0.f));
+                        u.w = pack_half2(fmaxf(v[j + 6], 0.f), fmaxf(v[j + 7], 0.f));
+                        *reinterpret_cast<uint4*>(op + j) = u;
+                    }
+                } else {
+                    for (int j = 0; j < 32 && n + j < p.cout; ++j) op[j] = __float2half_rn(fmaxf(v[j], 0.f));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, BN);
+}
+
+template <int BN>
+int launch_conv(const ConvMaps& maps, const ConvP& p, int cout_pad, cudaStream_t stream) {
+    tc5_debug_init();
+    static bool attr_done = false;
+    const int smem = (int)sizeof(ConvSmem<BN>) + 1024;
+    if (!attr_done) {
+        XM_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    dim3 grid(p.tiles_x * p.tiles_y * p.batch, cout_pad / BN);
+    conv_igemm_kernel<BN><<<grid, 192, smem, stream>>>(maps, p);
+    XM_CHECK_CUDA(cudaGetLastError());
+    return XM_OK;
+}
+
+}  // namespace
+
+extern "C" int xm_conv2d_nhwc(const xm_conv_args_t* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    XM_REQUIRE(a, "xm_conv2d_nhwc: null args");
+    XM_REQUIRE(a->n_src >= 1 && a->n_src <= 3, "xm_conv2d_nhwc: n_src must be 1..3");
+    XM_REQUIRE(a->ksize == 1 || a->ksize == 3, "xm_conv2d_nhwc: ksize must be 1 or 3");
+    XM_REQUIRE(a->stride == 1 || a->stride == 2, "xm_conv2d_nhwc: stride must be 1 or 2");
+    XM_REQUIRE(a->batch >= 1 && a->H > 0 && a->W > 0, "xm_conv2d_nhwc: bad shape");
+    XM_REQUIRE(a->cout >= 1 && a->cout_pad >= a->cout && a->cout_pad % 64 == 0, "xm_conv2d_nhwc: cout_pad must be a multiple of 64 >= cout");
+    XM_REQUIRE(a->weight && a->bias && (a->out || a->out_relu), "xm_conv2d_nhwc: null weight/bias/out");
+    XM_REQUIRE(a->out_stride >= a->out_offset + a->cout, "xm_conv2d_nhwc: out_stride too small");
+    if (a->stride == 2) {
+        XM_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, "xm_conv2d_nhwc: stride-2 needs even H, W");
+        XM_REQUIRE(a->batch == 1, "xm_conv2d_nhwc: stride-2 convolutions are launched one image at a time");
+    }
+    ConvP p;
+    p.n_src = a->n_src;
+    p.cin_total = 0;
+    for (int s = 0; s < 3; ++s) { p.cblocks[s] = 0; p.choff[s] = 0; p.bcast[s] = 0; }
+    for (int s = 0; s < a->n_src; ++s) {
+        XM_REQUIRE(a->src[s].ptr && a->src[s].channels > 0 && a->src[s].channels % 64 == 0,
+                   "xm_conv2d_nhwc: source %d channels must be a positive multiple of 64", s);
+        p.cblocks[s] = a->src[s].channels / 64;
+        p.choff[s] = p.cin_total;
+        p.bcast[s] = a->src[s].broadcast;
+        p.cin_total += a->src[s].channels;
+    }
+    p.ksize = a->ksize; p.stride = a->stride; p.pad = a->ksize / 2;
+    p.Ho = a->H / a->stride; p.Wo = a->W / a->stride; p.batch = a->batch;
+    // tile rectangle: minimise padded area
+    int best_tw = 16; long best = -1;
+    for (int tw = 8; tw <= 32; tw *= 2) {
+        const int th = 128 / tw;
+        long area = (long)((p.Wo + tw - 1) / tw) * ((p.Ho + th - 1) / th);
+        if (best < 0 || area < best) { best = area; best_tw = tw; }
+    }
+    p.tw = best_tw; p.th = 128 / best_tw;
+    p.tiles_x = (p.Wo + p.tw - 1) / p.tw; p.tiles_y = (p.Ho + p.th - 1) / p.th;
+    p.cout = a->cout; p.relu = a->relu; p.bias = a->bias;
+    p.residual = (const __half*)a->residual; p.residual_bcast = a->residual_broadcast; p.residual_stride = a->cout;
+    p.out = (__half*)a->out; p.out_relu = (__half*)a->out_relu; p.out_stride = a->out_stride; p.out_offset = a->out_offset;
+
+    ConvMaps maps;
+    for (int s = 0; s < 3; ++s) {
+        const int ss = s < a->n_src ? s : 0;
+        const uint64_t C = a->src[ss].channels;
+        const uint64_t nb = a->src[ss].broadcast ? 1 : a->batch;
+        if (a->stride == 1) {
+            uint64_t d[4] = {C, (uint64_t)a->W, (uint64_t)a->H, nb};
+            uint64_t st[3] = {C * 2, (uint64_t)a->W * C * 2, (uint64_t)a->H * a->W * C * 2};
+            uint32_t bx[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
+            if (xm_make_tmap_f16(&maps.a[s], a->src[ss].ptr, 4, d, st, bx)) return XM_ERR_CUDA;
+        } else {
+            uint64_t d[5] = {C, 2, (uint64_t)a->W / 2, 2, (uint64_t)a->H / 2};
+            uint64_t st[4] = {C * 2, 2 * C * 2, (uint64_t)a->W * C * 2, 2 * (uint64_t)a->W * C * 2};
+            uint32_t bx[5] = {64, 1, (uint32_t)p.tw, 1, (uint32_t)p.th};
+            if (xm_make_tmap_f16(&maps.a[s], a->src[ss].ptr, 5, d, st, bx)) return XM_ERR_CUDA;
+        }
+    }
+    const int BN = (a->cout_pad % 128 == 0) ? 128 : 64;
+    {
+        const uint64_t K = (uint64_t)a->ksize * a->ksize * p.cin_total;
+        uint64_t d[2] = {K, (uint64_t)a->cout_pad};
+        uint64_t st[1] = {K * 2};
+        uint32_t bx[2] = {64, (uint32_t)BN};
+        if (xm_make_tmap_f16(&maps.w, a->weight, 2, d, st, bx)) return XM_ERR_CUDA;
+    }
+    return BN == 128 ? launch_conv<128>(maps, p, a->cout_pad, stream) : launch_conv<64>(maps, p, a->cout_pad, stream);
+}

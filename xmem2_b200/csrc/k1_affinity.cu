@@ -1,0 +1,657 @@
+// k1_affinity.cu — fused memory read for XMem++:  similarity -> top-k softmax -> value readout (+usage)
+//
+// Replaces the reference sequence get_similarity (model/memory_util.py:7-39) -> do_softmax top-k branch
+// (:41-54, no max-subtraction) -> usage = affinity.sum (:62-63) -> v @ affinity (memory_manager.py:57-59)
+// over the concatenated long-term | working | permanent banks (memory_manager.py:82-128,143-182),
+// without ever materialising the N x HW similarity / affinity matrices.
+//
+// Math.  With packed operands  Kp[n] = (k_n^2 , k_n)  and  Qp[q] = (-e_q , 2 k_q e_q)  (fp16, 128 wide)
+//     S'[q,n] = Qp[q] . Kp[n] = -sum_c e k_n^2 + 2 sum_c k_n k_q e          (tcgen05.mma, fp32 accumulate)
+//     S[q,n]  = (S'[q,n] - bsq[q]) * shrinkage[n] / sqrt(64)                 (bsq = sum_c e k_q^2, fp32)
+// Pass 1 (k1_topk_pass1): every CTA owns 128 queries x one slice of memory columns, streams 64-column
+//     key tiles through TMA -> smem -> tcgen05 -> TMEM, and each of 128 threads keeps the running top-k of
+//     ITS query (one TMEM lane = one query).  k1_topk_merge combines the slices: tau[q] = k-th largest
+//     S, inv_den[q] = 1 / sum_topk exp(S).
+// Pass 2 (k1_readout_pass2): recomputes the same S tiles (bit-identical: same instruction stream), forms
+//     P = (S >= tau) ? exp(S) * inv_den : 0 as fp16 in shared memory, and accumulates
+//     O^T[c, q] += V[c, n-tile] . P[q, n-tile]^T  in TMEM (dense tensor-core contraction, as the
+//     reference's dense v @ affinity).  Split over column slices; k1_finish sums the slices.
+#include <cfloat>
+#include <cmath>
+#include "common.h"
+#include "tc5.cuh"
+
+using namespace tc5;
+
+namespace {
+
+constexpr int TQ = 128;          // queries per CTA (UMMA M / TMEM lanes)
+constexpr int TN = 64;           // memory columns per tile
+constexpr int KP = 128;          // packed key width
+constexpr int LISTK = XM_MAX_TOPK;
+constexpr int P1_STAGES = 4;
+constexpr int P1_SBUF = 4;
+constexpr int P2_KSTAGES = 3;
+constexpr int P2_VSTAGES = 3;
+constexpr int P2_SBUF = 2;
+constexpr int P2_PBUF = 2;
+constexpr int CHALF = 256;       // value channels per pass-2 CTA
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct alignas(64) K1Maps {
+    CUtensorMap q;       // [128, hw_pad]            box [64,128]
+    CUtensorMap k[3];    // [128, cap_b]             box [64, 64]
+    CUtensorMap v[3];    // [cap_b, 512, n_obj_cap]  box [64,128,1]
+};
+
+struct K1Seg {
+    int nseg;
+    int bank[3];
+    int begin[3];
+    int end[3];
+    int origin[3];       // begin rounded down to 8 columns: TMA needs 16-byte aligned starts on the contiguous (column) axis of V
+    int tile0[4];        // prefix sum of tiles per segment
+    int col0[3];         // first column of the segment inside the group's concatenated column index
+    const float* shr[3];
+    float* usage[3];
+};
+
+// tile t -> segment s, first column `col` of the 64-wide tile, valid lanes [lo, hi) inside the tile
+__device__ __forceinline__ void locate_tile(const K1Seg& sg, int t, int& s, int& col, int& lo, int& hi) {
+    s = 0;
+    if (sg.nseg > 1 && t >= sg.tile0[1]) s = 1;
+    if (sg.nseg > 2 && t >= sg.tile0[2]) s = 2;
+    col = sg.origin[s] + (t - sg.tile0[s]) * TN;
+    lo = max(0, sg.begin[s] - col);
+    hi = min(TN, sg.end[s] - col);
+}
+
+__device__ __forceinline__ float score(uint32_t acc_bits, float bsq, float ms) {
+    // (S' - b_sq) * shrinkage / sqrt(CK)   memory_util.py:27,35 (CK = 64 -> exact *0.125)
+    return (__uint_as_float(acc_bits) - bsq) * ms * 0.125f;
+}
+
+__device__ __forceinline__ float fast_exp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * LOG2E));
+    return y;
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand packing
+// ---------------------------------------------------------------------------------------------
+__global__ void query_pack_kernel(const __half* __restrict__ key, const __half* __restrict__ sel, int hw, int hw_pad,
+                                  __half* __restrict__ qp, float* __restrict__ bsq) {
+    // one warp per query row; lane handles channels lane, lane+32
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= hw_pad) return;
+    float acc = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int c = lane + 32 * h;
+        __half k = __float2half(0.f), e = __float2half(0.f);
+        if (row < hw) {
+            k = key[(size_t)row * XM_CK + c];
+            e = sel[(size_t)row * XM_CK + c];
+        }
+        __half ke = __hmul(k, e);                        // fp16 product, as qk*qe under autocast
+        qp[(size_t)row * KP + c] = __hneg(e);
+        qp[(size_t)row * KP + XM_CK + c] = __hadd(ke, ke);
+        float kf = __half2float(k);
+        acc += __half2float(e) * (kf * kf);              // fp32, memory_util.py:26
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) bsq[row] = acc;
+}
+
+__global__ void key_pack_kernel(const __half* __restrict__ key, int n, __half* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * XM_CK) return;
+    int row = i / XM_CK, c = i % XM_CK;
+    __half k = key[i];
+    float kf = __half2float(k);
+    dst[(size_t)row * KP + c] = __float2half_rn(kf * kf);    // mk.pow(2) in fp32 then fp16 for the GEMM
+    dst[(size_t)row * KP + XM_CK + c] = k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1: per-slice top-k candidates
+// ---------------------------------------------------------------------------------------------
+struct P1Smem {
+    alignas(1024) uint8_t q[2][TQ * 128];                 // 2 K-halves x (128 rows x 128 B)
+    alignas(1024) uint8_t k[P1_STAGES][2][TN * 128];      // per stage 2 K-halves x (64 rows x 128 B)
+    float list[LISTK][TQ];
+    alignas(8) uint64_t qfull;
+    uint64_t kfull[P1_STAGES], kempty[P1_STAGES];
+    uint64_t sfull[P1_SBUF], sempty[P1_SBUF];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(192, 1)
+k1_topk_pass1(const __grid_constant__ K1Maps maps, const K1Seg sg, const float* __restrict__ bsq, int hw, int hw_pad,
+              int top_k, int tiles_per_split, float* __restrict__ cand, float* __restrict__ dbg_scores) {
+    extern __shared__ uint8_t smem_raw[];
+    P1Smem& sm = *reinterpret_cast<P1Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qtile = blockIdx.x, split = blockIdx.y;
+    const int total_tiles = sg.tile0[sg.nseg];
+    const int t_begin = split * tiles_per_split;
+    const int t_end = min(total_tiles, t_begin + tiles_per_split);
+    const int nt = max(0, t_end - t_begin);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.qfull, 1);
+        for (int i = 0; i < P1_STAGES; ++i) { mbar_init(&sm.kfull[i], 1); mbar_init(&sm.kempty[i], 1); }
+        for (int i = 0; i < P1_SBUF; ++i) { mbar_init(&sm.sfull[i], 1); mbar_init(&sm.sempty[i], 128); }
+        fence_mbar_init();
+    }
+    if (warp == 1) { tmem_alloc(&sm.tmem_base, 256); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&maps.q);
+            mbar_expect_tx(&sm.qfull, 2 * TQ * 128);
+            tma_load_2d(sm.q[0], &maps.q, &sm.qfull, 0, qtile * TQ);
+            tma_load_2d(sm.q[1], &maps.q, &sm.qfull, 64, qtile * TQ);
+            for (int i = 0; i < nt; ++i) {
+                int s, col, lo, nv;
+                locate_tile(sg, t_begin + i, s, col, lo, nv);
+                const int st = i % P1_STAGES, ph = (i / P1_STAGES) & 1;
+                mbar_wait(&sm.kempty[st], ph ^ 1, 2);
+                mbar_expect_tx(&sm.kfull[st], 2 * TN * 128);
+                const CUtensorMap* km = &maps.k[sg.bank[s]];
+                tma_load_2d(sm.k[st][0], km, &sm.kfull[st], 0, col);
+                tma_load_2d(sm.k[st][1], km, &sm.kfull[st], 64, col);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(TQ, TN);
+            mbar_wait(&sm.qfull, 0, 1);
+            for (int i = 0; i < nt; ++i) {
+                const int st = i % P1_STAGES, ph = (i / P1_STAGES) & 1;
+                const int sb = i % P1_SBUF, sph = (i / P1_SBUF) & 1;
+                mbar_wait(&sm.kfull[st], ph, 3);
+                mbar_wait(&sm.sempty[sb], sph ^ 1, 4);
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint64_t a = make_desc_sw128(smem_u32(sm.q[h]) + j * 32);
+                        uint64_t b = make_desc_sw128(smem_u32(sm.k[st][h]) + j * 32);
+                        mma_f16_ss(tmem + sb * TN, a, b, idesc, (h | j) ? 1u : 0u);
+                    }
+                mma_commit(&sm.kempty[st]);
+                mma_commit(&sm.sfull[sb]);
+            }
+        }
+    } else {
+        // selection warps: one thread per query (TMEM lane)
+        const int lane_base = (warp & 3) * 32;
+        const int row = lane_base + lane;
+        const int q = qtile * TQ + row;
+        const float my_bsq = bsq[q];            // bsq is padded to hw_pad
+        for (int i = 0; i < LISTK; ++i) sm.list[i][row] = -INFINITY;
+        float cur_min = -INFINITY;
+        int cur_pos = 0;
+        for (int i = 0; i < nt; ++i) {
+            int s, col, lo, nv;
+            locate_tile(sg, t_begin + i, s, col, lo, nv);
+            const int sb = i % P1_SBUF, sph = (i / P1_SBUF) & 1;
+            mbar_wait(&sm.sfull[sb], sph, 5);
+            tc_fence_after();
+            uint32_t r0[32], r1[32];
+            const uint32_t taddr = tmem + (static_cast<uint32_t>(lane_base) << 16) + sb * TN;
+            tmem_ld_32x32b_x32(taddr, r0);
+            tmem_ld_32x32b_x32(taddr + 32, r1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&sm.sempty[sb]);
+            const float* shr = sg.shr[s] + col;
+            float* dbg = dbg_scores ? dbg_scores + ((ptrdiff_t)sg.col0[s] + (col - sg.begin[s])) * (ptrdiff_t)hw_pad + q : nullptr;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const bool valid = (j >= lo) && (j < nv);
+                const float ms = valid ? __ldg(shr + j) : 1.f;
+                float sc = score(j < 32 ? r0[j & 31] : r1[j & 31], my_bsq, ms);
+                if (!valid) sc = -INFINITY;
+                if (dbg && valid) dbg[(ptrdiff_t)j * hw_pad] = sc;
+                if (sc > cur_min) {
+                    sm.list[cur_pos][row] = sc;
+                    float m = sm.list[0][row];
+                    int p = 0;
+                    for (int u = 1; u < top_k; ++u) {
+                        float v = sm.list[u][row];
+                        if (v < m) { m = v; p = u; }
+                    }
+                    cur_min = m;
+                    cur_pos = p;
+                }
+            }
+        }
+        float* dst = cand + ((size_t)split * hw_pad + q) * LISTK;
+        for (int u = 0; u < LISTK; ++u) dst[u] = (u < top_k) ? sm.list[u][row] : -INFINITY;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// merge the per-slice candidate lists: one warp per query, lane l owns slice l (nsplit <= 32)
+__global__ void k1_topk_merge(const float* __restrict__ cand, int nsplit, int hw, int hw_pad, int top_k,
+                              float* __restrict__ tau, float* __restrict__ inv_den) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= hw_pad) return;
+    if (q >= hw) {                       // padded query rows never select anything
+        if (lane == 0) { tau[q] = INFINITY; inv_den[q] = 0.f; }
+        return;
+    }
+    float v[LISTK];
+#pragma unroll
+    for (int u = 0; u < LISTK; ++u) v[u] = -INFINITY;
+    if (lane < nsplit) {
+        const float4* src = reinterpret_cast<const float4*>(cand + ((size_t)lane * hw_pad + q) * LISTK);
+#pragma unroll
+        for (int u = 0; u < LISTK / 4; ++u) {
+            float4 f = src[u];
+            v[4 * u] = f.x; v[4 * u + 1] = f.y; v[4 * u + 2] = f.z; v[4 * u + 3] = f.w;
+        }
+    }
+    float den = 0.f, kth = -INFINITY;
+    for (int r = 0; r < top_k; ++r) {
+        float m = v[0];
+#pragma unroll
+        for (int u = 1; u < LISTK; ++u) m = fmaxf(m, v[u]);
+        float g = m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, o));
+        const unsigned owners = __ballot_sync(0xffffffffu, m == g);
+        if (lane == __ffs(owners) - 1) {
+            bool done = false;
+#pragma unroll
+            for (int u = 0; u < LISTK; ++u)
+                if (!done && v[u] == g) { v[u] = -INFINITY; done = true; }
+        }
+        den += fast_exp(g);
+        kth = g;
+    }
+    if (lane == 0) { tau[q] = kth; inv_den[q] = 1.f / den; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2: P = (S >= tau) ? exp(S) / den : 0 ;  O^T[c,q] += V[c,n] P[q,n]
+// ---------------------------------------------------------------------------------------------
+struct P2Smem {
+    alignas(1024) uint8_t q[2][TQ * 128];
+    alignas(1024) uint8_t k[P2_KSTAGES][2][TN * 128];
+    alignas(1024) uint8_t v[P2_VSTAGES][2][128 * 128];    // 2 M-chunks x (128 channel rows x 64 columns)
+    alignas(1024) uint8_t p[P2_PBUF][TQ * 128];           // 128 query rows x 64 columns fp16
+    alignas(8) uint64_t qfull;
+    uint64_t kfull[P2_KSTAGES], kempty[P2_KSTAGES];
+    uint64_t vfull[P2_VSTAGES], vempty[P2_VSTAGES];
+    uint64_t sfull[P2_SBUF], sempty[P2_SBUF];
+    uint64_t pfull[P2_PBUF], pempty[P2_PBUF];
+    uint64_t ofull;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(192, 1)
+k1_readout_pass2(const __grid_constant__ K1Maps maps, const K1Seg sg, const float* __restrict__ bsq,
+                 const float* __restrict__ tau, const float* __restrict__ inv_den, int hw_pad, int obj_begin,
+                 int n_obj, int tiles_per_split, int do_usage, float* __restrict__ partial) {
+    extern __shared__ uint8_t smem_raw[];
+    P2Smem& sm = *reinterpret_cast<P2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qtile = blockIdx.x;
+    const int obj = blockIdx.y >> 1, chalf = blockIdx.y & 1;       // local object index within the group
+    const int split = blockIdx.z;
+    const int total_tiles = sg.tile0[sg.nseg];
+    const int t_begin = split * tiles_per_split;
+    const int t_end = min(total_tiles, t_begin + tiles_per_split);
+    const int nt = max(0, t_end - t_begin);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.qfull, 1);
+        for (int i = 0; i < P2_KSTAGES; ++i) { mbar_init(&sm.kfull[i], 1); mbar_init(&sm.kempty[i], 1); }
+        for (int i = 0; i < P2_VSTAGES; ++i) { mbar_init(&sm.vfull[i], 1); mbar_init(&sm.vempty[i], 1); }
+        for (int i = 0; i < P2_SBUF; ++i) { mbar_init(&sm.sfull[i], 1); mbar_init(&sm.sempty[i], 128); }
+        for (int i = 0; i < P2_PBUF; ++i) { mbar_init(&sm.pfull[i], 128); mbar_init(&sm.pempty[i], 1); }
+        mbar_init(&sm.ofull, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) { tmem_alloc(&sm.tmem_base, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    const uint32_t tmem_s = tmem + 256;        // S buffers after the two 128-column O^T chunks
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(&sm.qfull, 2 * TQ * 128);
+            tma_load_2d(sm.q[0], &maps.q, &sm.qfull, 0, qtile * TQ);
+            tma_load_2d(sm.q[1], &maps.q, &sm.qfull, 64, qtile * TQ);
+            for (int i = 0; i < nt; ++i) {
+                int s, col, lo, nv;
+                locate_tile(sg, t_begin + i, s, col, lo, nv);
+                const int b = sg.bank[s];
+                {
+                    const int st = i % P2_KSTAGES, ph = (i / P2_KSTAGES) & 1;
+                    mbar_wait(&sm.kempty[st], ph ^ 1, 2);
+                    mbar_expect_tx(&sm.kfull[st], 2 * TN * 128);
+                    tma_load_2d(sm.k[st][0], &maps.k[b], &sm.kfull[st], 0, col);
+                    tma_load_2d(sm.k[st][1], &maps.k[b], &sm.kfull[st], 64, col);
+                }
+                {
+                    const int st = i % P2_VSTAGES, ph = (i / P2_VSTAGES) & 1;
+                    mbar_wait(&sm.vempty[st], ph ^ 1, 6);
+                    mbar_expect_tx(&sm.vfull[st], 2 * 128 * 128);
+                    tma_load_3d(sm.v[st][0], &maps.v[b], &sm.vfull[st], col, chalf * CHALF, obj_begin + obj);
+                    tma_load_3d(sm.v[st][1], &maps.v[b], &sm.vfull[st], col, chalf * CHALF + 128, obj_begin + obj);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_f16(TQ, TN);
+            constexpr uint32_t idesc_o = make_idesc_f16(128, TQ);
+            mbar_wait(&sm.qfull, 0, 1);
+            for (int i = 0; i <= nt; ++i) {
+                if (i < nt) {          // S(i) = Qp . Kp^T
+                    const int st = i % P2_KSTAGES, ph = (i / P2_KSTAGES) & 1;
+                    const int sb = i % P2_SBUF, sph = (i / P2_SBUF) & 1;
+                    mbar_wait(&sm.kfull[st], ph, 3);
+                    mbar_wait(&sm.sempty[sb], sph ^ 1, 4);
+                    tc_fence_after();
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint64_t a = make_desc_sw128(smem_u32(sm.q[h]) + j * 32);
+                            uint64_t b = make_desc_sw128(smem_u32(sm.k[st][h]) + j * 32);
+                            mma_f16_ss(tmem_s + sb * TN, a, b, idesc_s, (h | j) ? 1u : 0u);
+                        }
+                    mma_commit(&sm.kempty[st]);
+                    mma_commit(&sm.sfull[sb]);
+                }
+                if (i > 0) {           // O^T += V(i-1) . P(i-1)^T
+                    const int u = i - 1;
+                    const int vs = u % P2_VSTAGES, vph = (u / P2_VSTAGES) & 1;
+                    const int pb = u % P2_PBUF, pph = (u / P2_PBUF) & 1;
+                    mbar_wait(&sm.vfull[vs], vph, 7);
+                    mbar_wait(&sm.pfull[pb], pph, 8);
+                    tc_fence_after();
+#pragma unroll
+                    for (int m = 0; m < 2; ++m)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint64_t a = make_desc_sw128(smem_u32(sm.v[vs][m]) + j * 32);
+                            uint64_t b = make_desc_sw128(smem_u32(sm.p[pb]) + j * 32);
+                            mma_f16_ss(tmem + m * 128, a, b, idesc_o, (u > 0 || j > 0) ? 1u : 0u);
+                        }
+                    mma_commit(&sm.vempty[vs]);
+                    mma_commit(&sm.pempty[pb]);
+                }
+            }
+            mma_commit(&sm.ofull);
+        }
+    } else {
+        const int lane_base = (warp & 3) * 32;
+        const int row = lane_base + lane;
+        const int q = qtile * TQ + row;
+        const float my_bsq = bsq[q];
+        const float my_tau = tau[q];
+        const float my_inv = inv_den[q];
+        const bool usage_cta = do_usage && blockIdx.y == 0;
+        for (int i = 0; i < nt; ++i) {
+            int s, col, lo, nv;
+            locate_tile(sg, t_begin + i, s, col, lo, nv);
+            const int sb = i % P2_SBUF, sph = (i / P2_SBUF) & 1;
+            const int pb = i % P2_PBUF, pph = (i / P2_PBUF) & 1;
+            mbar_wait(&sm.sfull[sb], sph, 5);
+            tc_fence_after();
+            uint32_t r0[32], r1[32];
+            const uint32_t taddr = tmem_s + (static_cast<uint32_t>(lane_base) << 16) + sb * TN;
+            tmem_ld_32x32b_x32(taddr, r0);
+            tmem_ld_32x32b_x32(taddr + 32, r1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&sm.sempty[sb]);
+            const float* shr = sg.shr[s] + col;
+            float* usage = (usage_cta && sg.usage[s]) ? sg.usage[s] + col : nullptr;
+            uint32_t packed[32];
+#pragma unroll
+            for (int j = 0; j < TN; j += 2) {
+                float pv[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int jj = j + e;
+                    const bool valid = (jj >= lo) && (jj < nv);
+                    const float ms = valid ? __ldg(shr + jj) : 1.f;
+                    const float sc = score(jj < 32 ? r0[jj & 31] : r1[jj & 31], my_bsq, ms);
+                    float p = 0.f;
+                    if (valid && sc >= my_tau) {
+                        p = fast_exp(sc) * my_inv;
+                        if (usage) atomicAdd(usage + jj, p);
+                    }
+                    pv[e] = p;
+                }
+                packed[j >> 1] = pack_half2(pv[0], pv[1]);
+            }
+            mbar_wait(&sm.pempty[pb], pph ^ 1, 9);
+            uint8_t* prow = sm.p[pb] + row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint4 val = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+                *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = val;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&sm.pfull[pb]);
+        }
+        // epilogue: O^T chunk m, lane = channel, columns = queries
+        mbar_wait(&sm.ofull, 0, 10);
+        tc_fence_after();
+        const int n_obj_all = gridDim.y >> 1;
+        (void)n_obj;
+#pragma unroll 1
+        for (int m = 0; m < 2; ++m) {
+            const int c = chalf * CHALF + m * 128 + row;
+            float* dst = partial + (((size_t)split * n_obj_all + obj) * XM_CV + c) * hw_pad + qtile * TQ;
+#pragma unroll 1
+            for (int qq = 0; qq < 4; ++qq) {
+                uint32_t r[32];
+                if (nt > 0) {
+                    tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(lane_base) << 16) + m * 128 + qq * 32, r);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(dst + qq * 32 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// sum the column slices, convert to fp16, write CHW and/or HWC
+__global__ void k1_finish(const float* __restrict__ partial, int nsplit, int n_obj, int hw, int hw_pad, int obj_begin,
+                          __half* __restrict__ out_chw, __half* __restrict__ out_hwc) {
+    __shared__ float tile[32][33];
+    const int o = blockIdx.z;
+    const int c0 = blockIdx.y * 32, q0 = blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;       // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, q = q0 + tx;
+        float acc = 0.f;
+        if (q < hw)
+            for (int s = 0; s < nsplit; ++s) acc += partial[(((size_t)s * n_obj + o) * XM_CV + c) * hw_pad + q];
+        tile[r][tx] = acc;
+        if (out_chw && q < hw) out_chw[((size_t)(obj_begin + o) * XM_CV + c) * hw + q] = __float2half_rn(acc);
+    }
+    if (out_hwc) {
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int q = q0 + r, c = c0 + tx;
+            if (q < hw) out_hwc[((size_t)(obj_begin + o) * hw + q) * XM_CV + c] = __float2half_rn(tile[tx][r]);
+        }
+    }
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int xm_query_pack(const void* key_hwc, const void* sel_hwc, int32_t hw, int32_t hw_pad, void* qp, float* bsq,
+                             void* stream) {
+    XM_REQUIRE(key_hwc && sel_hwc && qp && bsq, "xm_query_pack: null pointer");
+    XM_REQUIRE(hw > 0 && hw_pad >= hw && hw_pad % TQ == 0, "xm_query_pack: hw_pad must be a multiple of 128 and >= hw");
+    const int warps = 8;
+    query_pack_kernel<<<(hw_pad + warps - 1) / warps, warps * 32, 0, (cudaStream_t)stream>>>(
+        (const __half*)key_hwc, (const __half*)sel_hwc, hw, hw_pad, (__half*)qp, bsq);
+    XM_CHECK_CUDA(cudaGetLastError());
+    return XM_OK;
+}
+
+extern "C" int xm_key_pack(const void* key_hwc, int32_t n, void* dst_rows, void* stream) {
+    XM_REQUIRE(key_hwc && dst_rows && n >= 0, "xm_key_pack: bad arguments");
+    if (n == 0) return XM_OK;
+    const int total = n * XM_CK;
+    key_pack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const __half*)key_hwc, n, (__half*)dst_rows);
+    XM_CHECK_CUDA(cudaGetLastError());
+    return XM_OK;
+}
+
+static const int K1_MAX_SPLIT = 32;
+
+extern "C" int64_t xm_affinity_workspace_bytes(int32_t hw, int32_t n_obj_total) {
+    const int64_t hw_pad = (hw + TQ - 1) / TQ * TQ;
+    int64_t b = 0;
+    b += align_up((size_t)K1_MAX_SPLIT * hw_pad * LISTK * 4, 256);        // candidates
+    b += 2 * align_up((size_t)hw_pad * 4, 256);                           // tau, inv_den
+    b += align_up((size_t)K1_MAX_SPLIT * n_obj_total * XM_CV * hw_pad * 4, 256);   // partial readouts
+    return b;
+}
+
+extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    XM_REQUIRE(a, "xm_affinity_readout: null args");
+    XM_REQUIRE(a->hw > 0 && a->hw_pad == (a->hw + TQ - 1) / TQ * TQ, "xm_affinity_readout: hw_pad must be hw rounded up to 128");
+    XM_REQUIRE(a->top_k > 0 && a->top_k <= XM_MAX_TOPK, "xm_affinity_readout: top_k must be in [1,%d]", XM_MAX_TOPK);
+    XM_REQUIRE(a->n_groups > 0 && a->n_groups <= XM_MAX_GROUPS, "xm_affinity_readout: bad n_groups %d", a->n_groups);
+    XM_REQUIRE(a->qp && a->bsq && a->workspace, "xm_affinity_readout: null query/workspace");
+    XM_REQUIRE(a->readout_chw || a->readout_hwc, "xm_affinity_readout: no output buffer");
+    XM_REQUIRE(a->workspace_bytes >= xm_affinity_workspace_bytes(a->hw, a->n_obj_total), "xm_affinity_readout: workspace too small");
+    const int hw = a->hw, hw_pad = a->hw_pad;
+    const int qtiles = hw_pad / TQ;
+
+    tc5_debug_init();
+    static bool attr_done = false;
+    if (!attr_done) {
+        XM_CHECK_CUDA(cudaFuncSetAttribute(k1_topk_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P1Smem) + 1024));
+        XM_CHECK_CUDA(cudaFuncSetAttribute(k1_readout_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2Smem) + 1024));
+        attr_done = true;
+    }
+
+    K1Maps maps;
+    {
+        uint64_t d[2] = {KP, (uint64_t)hw_pad};
+        uint64_t s[1] = {KP * 2};
+        uint32_t b[2] = {64, TQ};
+        if (xm_make_tmap_f16(&maps.q, a->qp, 2, d, s, b)) return XM_ERR_CUDA;
+    }
+    for (int i = 0; i < 3; ++i) {
+        const xm_bank_t& bk = a->banks[i];
+        if (bk.size <= 0 || !bk.keys) {     // unused bank: alias the query map so the struct is fully initialised
+            maps.k[i] = maps.q;
+            maps.v[i] = maps.q;
+            continue;
+        }
+        XM_REQUIRE(bk.cap % 8 == 0 && bk.size <= bk.cap, "xm_affinity_readout: bank %d cap must be a multiple of 8 and >= size", i);
+        XM_REQUIRE(bk.shrinkage && bk.values && bk.n_obj_cap > 0, "xm_affinity_readout: bank %d has null shrinkage/values", i);
+        uint64_t d[2] = {KP, (uint64_t)bk.cap};
+        uint64_t s[1] = {KP * 2};
+        uint32_t b[2] = {64, TN};
+        if (xm_make_tmap_f16(&maps.k[i], bk.keys, 2, d, s, b)) return XM_ERR_CUDA;
+        uint64_t dv[3] = {(uint64_t)bk.cap, XM_CV, (uint64_t)bk.n_obj_cap};
+        uint64_t sv[2] = {(uint64_t)bk.cap * 2, (uint64_t)bk.cap * 2 * XM_CV};
+        uint32_t bv[3] = {TN, 128, 1};
+        if (xm_make_tmap_f16(&maps.v[i], bk.values, 3, dv, sv, bv)) return XM_ERR_CUDA;
+    }
+
+    uint8_t* ws = (uint8_t*)a->workspace;
+    float* cand = (float*)ws;            ws += align_up((size_t)K1_MAX_SPLIT * hw_pad * LISTK * 4, 256);
+    float* tau = (float*)ws;             ws += align_up((size_t)hw_pad * 4, 256);
+    float* inv_den = (float*)ws;         ws += align_up((size_t)hw_pad * 4, 256);
+    float* partial = (float*)ws;
+
+    const int sms = xm_num_sms();
+    for (int g = 0; g < a->n_groups; ++g) {
+        const xm_group_t& gr = a->groups[g];
+        XM_REQUIRE(gr.n_obj > 0 && gr.obj_begin >= 0 && gr.obj_begin + gr.n_obj <= a->n_obj_total, "xm_affinity_readout: bad group %d objects", g);
+        K1Seg sg;
+        sg.nseg = 0;
+        int tiles = 0, cols = 0;
+        for (int i = 0; i < 3; ++i) {
+            const xm_bank_t& bk = a->banks[i];
+            sg.shr[i] = nullptr; sg.usage[i] = nullptr; sg.bank[i] = 0; sg.begin[i] = 0; sg.end[i] = 0; sg.col0[i] = 0; sg.origin[i] = 0;
+            if (bk.size <= 0 || !bk.keys) continue;
+            const int begin = gr.begin[i];
+            XM_REQUIRE(begin >= 0 && begin <= bk.size, "xm_affinity_readout: group %d bank %d begin %d outside [0,%d]", g, i, begin, bk.size);
+            if (begin == bk.size) continue;
+            XM_REQUIRE(gr.obj_begin + gr.n_obj <= bk.n_obj_cap, "xm_affinity_readout: bank %d holds fewer value planes than group %d needs", i, g);
+            const int s = sg.nseg++;
+            sg.bank[s] = i; sg.begin[s] = begin; sg.end[s] = bk.size; sg.tile0[s] = tiles; sg.col0[s] = cols;
+            sg.origin[s] = begin & ~7;
+            sg.shr[s] = bk.shrinkage; sg.usage[s] = (g == 0) ? bk.usage : nullptr;
+            tiles += (bk.size - sg.origin[s] + TN - 1) / TN;
+            cols += bk.size - begin;
+        }
+        for (int s = sg.nseg; s < 4; ++s) sg.tile0[s] = tiles;
+        XM_REQUIRE(cols >= a->top_k, "xm_affinity_readout: group %d sees %d memory columns < top_k=%d (torch.topk would raise)", g, cols, a->top_k);
+
+        // pass 1
+        int nsplit1 = (sms + qtiles - 1) / qtiles;
+        nsplit1 = nsplit1 < 1 ? 1 : nsplit1;
+        if (nsplit1 > K1_MAX_SPLIT) nsplit1 = K1_MAX_SPLIT;
+        if (nsplit1 > tiles) nsplit1 = tiles;
+        int tps1 = (tiles + nsplit1 - 1) / nsplit1;
+        nsplit1 = (tiles + tps1 - 1) / tps1;
+        k1_topk_pass1<<<dim3(qtiles, nsplit1), 192, sizeof(P1Smem) + 1024, stream>>>(
+            maps, sg, a->bsq, hw, hw_pad, a->top_k, tps1, cand, g == 0 ? a->debug_scores : nullptr);
+        XM_CHECK_CUDA(cudaGetLastError());
+        k1_topk_merge<<<(hw_pad + 3) / 4, 128, 0, stream>>>(cand, nsplit1, hw, hw_pad, a->top_k, tau, inv_den);
+        XM_CHECK_CUDA(cudaGetLastError());
+
+        // pass 2
+        const int ctas_per_slice = qtiles * 2 * gr.n_obj;
+        int nsplit2 = (sms + ctas_per_slice - 1) / ctas_per_slice;
+        nsplit2 = nsplit2 < 1 ? 1 : nsplit2;
+        if (nsplit2 > K1_MAX_SPLIT) nsplit2 = K1_MAX_SPLIT;
+        if (nsplit2 > tiles) nsplit2 = tiles;
+        int tps2 = (tiles + nsplit2 - 1) / nsplit2;
+        nsplit2 = (tiles + tps2 - 1) / tps2;
+        k1_readout_pass2<<<dim3(qtiles, 2 * gr.n_obj, nsplit2), 192, sizeof(P2Smem) + 1024, stream>>>(
+            maps, sg, a->bsq, tau, inv_den, hw_pad, gr.obj_begin, gr.n_obj, tps2, g == 0 ? 1 : 0, partial);
+        XM_CHECK_CUDA(cudaGetLastError());
+        k1_finish<<<dim3((hw + 31) / 32, XM_CV / 32, gr.n_obj), dim3(32, 8), 0, stream>>>(
+            partial, nsplit2, gr.n_obj, hw, hw_pad, gr.obj_begin, (__half*)a->readout_chw, (__half*)a->readout_hwc);
+        XM_CHECK_CUDA(cudaGetLastError());
+    }
+    return XM_OK;
+}
