@@ -109,6 +109,33 @@ typedef struct {
 
 int xm_conv2d_nhwc(const xm_conv_args_t* args, void* stream);
 
+/* ---------------------------------------------------------------- element-wise / small kernels (K5) */
+/* 7x7 stride-2 stem patches: image fp32 [3][H][W]; masks fp32 [n][H][W] or NULL (key encoder).
+ * out fp16 [n][H/2][W/2][kpad], k = (kh*7+kw)*C + c with C = 3 (image) or 5 (image, mask_b, sum of other masks):
+ * model/resnet.py:120 and ValueEncoder.forward model/modules.py:124-135.                                 */
+int xm_im2col_stem(const float* image, const float* masks, int32_t n, int32_t H, int32_t W, int32_t kpad, void* out, void* stream);
+/* nn.MaxPool2d(3, 2, 1) on NHWC fp16; relu != 0 applies ReLU after the pool (modules.py:137-138).        */
+int xm_maxpool3x3s2(const void* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t relu, void* out, void* stream);
+int xm_relu(const void* in, void* out, int64_t n, void* stream);
+/* proj fp16 [hw][pstride] = (key 0..63 | d 64 | e 65..128) -> key, selection = sigmoid(e) fp16 [hw][64],
+ * shrinkage = d^2+1 fp32 [hw] (modules.py:207-211) and, if qp != NULL, the packed query (see xm_query_pack). */
+int xm_keyproj_post(const void* proj, int32_t pstride, int32_t hw, int32_t hw_pad, void* key, void* sel, float* shr,
+                    void* qp, float* bsq, void* stream);
+/* out = x + CBAM(x) (model/cbam.py:66-77 and the "+ r" of modules.py:38-39); out_relu optional.
+ * scratch: (3*B*C + 2*B*H*W) floats.  w1 [C/16][C], b1 [C/16], w2 [C][C/16], b2 [C], w7 [2][7][7].        */
+int xm_cbam(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, const float* w1, const float* b1, const float* w2,
+            const float* b2, const float* w7, float b7, float* scratch, void* out, void* out_relu, void* stream);
+/* out = bilinear_x2(g [B][h][w][C]) + skip [1][2h][2w][C] (modules.py:186-189); out_relu optional.       */
+int xm_upsample2x_add(const void* g, const void* skip, int32_t B, int32_t h, int32_t w, int32_t C, void* out, void* out_relu, void* stream);
+/* area (mean) down-sampling by f; optional extra single-channel map appended as channel C; zero padded to cpad */
+int xm_area_down(const void* in, const void* extra, int32_t B, int32_t H, int32_t W, int32_t C, int32_t f, int32_t cpad, void* out, void* stream);
+/* values fp16 [npix][3*hd], h fp32 [npix][hd] -> h' = f*h*(1-u) + u*tanh(v) (modules.py:68-72) as fp32 and fp16 */
+int xm_gru(const void* values, const float* h, int64_t npix, int32_t hidden_dim, float* h_out, void* h_out16, void* stream);
+/* logits4 fp16 [n][h4][w4] -> bilinear x4, sigmoid, soft aggregation: prob/logits fp32 [n+1][4*h4][4*w4]  */
+int xm_upsample4x_aggregate(const void* logits4, int32_t n, int32_t h4, int32_t w4, float* prob, float* logits, void* stream);
+/* value fp16 [n_obj][hw][512] (NHWC) -> arena fp16 [n_obj][512][cap] columns [col0, col0+hw)               */
+int xm_value_append(const void* value_hwc, int32_t n_obj, int32_t hw, void* arena, int64_t cap, int32_t col0, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

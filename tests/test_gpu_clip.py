@@ -1,0 +1,94 @@
+"""End-to-end GPU parity: InferenceCore.step / put_to_permanent_memory traces on the synthetic clips whose
+expected outputs were produced by the LIVE reference (tests/golden/make_golden.py): memory-bank sizes per frame
+(bit-exact), object-group layout, probabilities, argmax maps, hidden state, usage statistics.
+Covers working-memory growth, consolidation into long-term prototypes, least-used eviction, and a second object
+group with suffix value ranges (reference inference/inference_core.py:62-179, memory_manager.py:61-390)."""
+import os
+import numpy as np
+import pytest
+import torch
+
+from xmem2_b200.inference.inference_core import InferenceCore
+from xmem2_b200.model.network import XMem
+from xmem2_b200.util.synth import synth_state_dict, synth_frame, synth_mask
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), 'golden')
+torch.set_grad_enabled(False)
+
+BASE = dict(mem_every=10, deep_update_every=-1, enable_long_term=True, enable_long_term_count_usage=True, hidden_dim=64,
+            key_dim=64, value_dim=512, top_k=30, max_mid_term_frames=10, min_mid_term_frames=5, num_prototypes=128,
+            max_long_term_elements=10000)
+
+
+@pytest.fixture(scope='module')
+def net():
+    n = XMem({}, None).to('cuda').eval()
+    n.load_weights(synth_state_dict(0))
+    return n
+
+
+def _run(net, name):
+    dev = 'cuda'
+    d = np.load(os.path.join(G, f'clip_{name}.npz'))
+    H, W, n_frames, n_obj, save_every = [int(x) for x in d['hw']]
+    cfg = dict(BASE); cfg.update({str(k): int(v) for k, v in zip(d['cfg_keys'], d['cfg_vals'])})
+    ffo = [int(x) for x in d['first_frame_of']]; annotated = [int(x) for x in d['annotated']]
+    core = InferenceCore(net, cfg)
+    n_seen = 0
+    for j in [int(x) for x in d['order']]:
+        n_seen = max(n_seen, sum(1 for f in ffo if f <= j))
+        core.set_all_labels(list(range(1, n_seen + 1)))
+        core.put_to_permanent_memory(synth_frame(j, H, W, structured=True).to(dev), synth_mask(j, H, W, n_obj, ffo)[:n_seen].to(dev))
+    labels = list(range(1, n_seen + 1))
+    k, worst_mean, worst_agree = 0, 0.0, 1.0
+    for ti in range(n_frames):
+        msk = synth_mask(ti, H, W, n_obj, ffo).to(dev) if ti in annotated else None
+        p = core.step(synth_frame(ti, H, W, structured=True).to(dev), msk, labels if msk is not None else None,
+                      end=(ti == n_frames - 1), do_not_add_mask_to_memory=msk is not None)
+        assert p.shape == (n_obj + 1, H, W)
+        m = core.memory
+        assert [m.temporary_work_mem.size, m.permanent_work_mem.size, m.long_mem.size] == d['sizes'][ti][:3].tolist(), ti
+        if ti % save_every == 0:
+            ref = torch.from_numpy(d['probs'][k]).float(); k += 1
+            e = (p.float().cpu() - ref).abs()
+            worst_mean = max(worst_mean, e.mean().item())
+            worst_agree = min(worst_agree, (p.argmax(0).cpu() == ref.argmax(0)).float().mean().item())
+    m = core.memory
+    assert m.permanent_work_mem.num_groups == int(d['sizes'][-1][3])
+    for g in range(m.permanent_work_mem.num_groups):
+        assert m.permanent_work_mem.get_v_size(g) == int(d['sizes'][-1][4 + g])
+    # fp16 tensor-core pipeline vs the fp32 reference trace (see tests/test_gpu_network.py for the calibration)
+    assert worst_mean < 1e-2, worst_mean
+    assert worst_agree > 0.95, worst_agree
+    hid = m.get_hidden().float().cpu()
+    assert (hid - torch.from_numpy(d['final_hidden']).float()).abs().mean().item() < 5e-3
+    if len(d['temp_usage']):
+        u = m.temporary_work_mem.get_usage().float().cpu()
+        assert (u - torch.from_numpy(d['temp_usage'])).abs().max().item() < 3e-2
+    return core
+
+
+def test_one_object_long_term_consolidation_and_eviction(net):
+    core = _run(net, 'one_obj')
+    assert core.memory.long_mem.size == 72          # 56 survivors + 16 new prototypes (golden: measured on the reference)
+
+
+def test_two_objects_two_groups(net):
+    core = _run(net, 'two_obj')
+    assert core.memory.permanent_work_mem.obj_groups == [[0], [1]]
+
+
+def test_disable_memory_updates_does_not_advance_state(net):
+    dev = 'cuda'
+    H, W = 64, 96
+    core = InferenceCore(net, dict(BASE))
+    core.set_all_labels([1])
+    core.put_to_permanent_memory(synth_frame(0, H, W, structured=True).to(dev), synth_mask(0, H, W, 1).to(dev))
+    core.step(synth_frame(0, H, W, structured=True).to(dev), synth_mask(0, H, W, 1).to(dev), [1], do_not_add_mask_to_memory=True)
+    ti, use = core.curr_ti, core.memory.permanent_work_mem.size
+    hidden = core.memory.get_hidden().clone()
+    p = core.step(synth_frame(1, H, W, structured=True).to(dev), disable_memory_updates=True)
+    assert core.curr_ti == ti and core.memory.permanent_work_mem.size == use
+    assert torch.equal(core.memory.get_hidden(), hidden)
+    assert torch.isfinite(p).all() and abs(p.sum(0).mean().item() - 1.0) < 1e-3

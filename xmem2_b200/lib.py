@@ -67,6 +67,18 @@ def load() -> C.CDLL:
         lib.xm_query_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.xm_key_pack.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.xm_conv2d_nhwc.argtypes = [C.POINTER(XmConvArgs), C.c_void_p]
+        vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+        lib.xm_debug_last_trap.argtypes = [C.POINTER(C.c_int)]
+        lib.xm_im2col_stem.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+        lib.xm_maxpool3x3s2.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
+        lib.xm_relu.argtypes = [vp, vp, i64, vp]
+        lib.xm_keyproj_post.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+        lib.xm_cbam.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp]
+        lib.xm_upsample2x_add.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp]
+        lib.xm_area_down.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+        lib.xm_gru.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+        lib.xm_upsample4x_aggregate.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+        lib.xm_value_append.argtypes = [vp, i32, i32, vp, i64, i32, vp]
         _lib = lib
     return _lib
 
