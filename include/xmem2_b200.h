@@ -36,6 +36,8 @@ const char* xm_last_error(void);
 int xm_version(void);
 /* diagnostics: {valid, tag, blockIdx.xyz, threadIdx.x, parity} of the last mbarrier-timeout trap */
 int xm_debug_last_trap(int* out7);
+/* number of kernels this library has launched so far (accounting for bench.py) */
+long long xm_launch_count(void);
 
 /* ---------------------------------------------------------------- memory read (K1) */
 /* One memory bank (KeyValueMemoryStore, inference/kv_memory_store.py:4-239) as the kernel sees it. */
@@ -105,6 +107,9 @@ typedef struct {
     void* out_relu;         /* optional second copy with ReLU applied (GroupResBlock needs g and relu(g)) */
     int32_t out_stride;     /* channel stride of out/out_relu (>= cout)                                 */
     int32_t out_offset;     /* first channel written                                                    */
+    void* workspace;        /* optional split-K scratch: 256 KiB of ZEROED int32 counters followed by fp32 partial
+                               tiles; NULL disables split-K.  The kernel leaves the counters zeroed.             */
+    int64_t workspace_bytes;
 } xm_conv_args_t;
 
 int xm_conv2d_nhwc(const xm_conv_args_t* args, void* stream);
@@ -122,7 +127,7 @@ int xm_relu(const void* in, void* out, int64_t n, void* stream);
 int xm_keyproj_post(const void* proj, int32_t pstride, int32_t hw, int32_t hw_pad, void* key, void* sel, float* shr,
                     void* qp, float* bsq, void* stream);
 /* out = x + CBAM(x) (model/cbam.py:66-77 and the "+ r" of modules.py:38-39); out_relu optional.
- * scratch: (3*B*C + 2*B*H*W) floats.  w1 [C/16][C], b1 [C/16], w2 [C][C/16], b2 [C], w7 [2][7][7].        */
+ * scratch: (33*B*C + 2*B*H*W) floats.  w1 [C/16][C], b1 [C/16], w2 [C][C/16], b2 [C], w7 [2][7][7].        */
 int xm_cbam(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, const float* w1, const float* b1, const float* w2,
             const float* b2, const float* w7, float b7, float* scratch, void* out, void* out_relu, void* stream);
 /* out = bilinear_x2(g [B][h][w][C]) + skip [1][2h][2w][C] (modules.py:186-189); out_relu optional.       */

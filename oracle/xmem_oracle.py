@@ -273,7 +273,7 @@ class OracleStore:
 
     def add(self, key, value, shrinkage, selection, objects):   # :36-94
         n_new = key.shape[2]
-        cnt = torch.zeros((1, 1, n_new)); life = torch.zeros((1, 1, n_new)) + 1e-7
+        cnt = torch.zeros((1, 1, n_new), device=key.device); life = torch.zeros((1, 1, n_new), device=key.device) + 1e-7
         if self.k is None:
             self.k, self.s, self.e = key, shrinkage, selection
             if self.count_usage:
@@ -446,9 +446,9 @@ class OracleMemory:
     def ensure_hidden(self, n, sample_key):         # :283-296
         h, w = sample_key.shape[-2:]
         if self.hidden is None:
-            self.hidden = torch.zeros((1, n, self.hidden_dim, h, w))
+            self.hidden = torch.zeros((1, n, self.hidden_dim, h, w), device=sample_key.device)
         elif self.hidden.shape[1] != n:
-            self.hidden = torch.cat([self.hidden, torch.zeros((1, n - self.hidden.shape[1], self.hidden_dim, h, w))], 1)
+            self.hidden = torch.cat([self.hidden, torch.zeros((1, n - self.hidden.shape[1], self.hidden_dim, h, w), device=sample_key.device)], 1)
 
 
 # ----------------------------------------------------------------------------------------------

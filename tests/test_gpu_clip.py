@@ -64,8 +64,11 @@ def _run(net, name):
     hid = m.get_hidden().float().cpu()
     assert (hid - torch.from_numpy(d['final_hidden']).float()).abs().mean().item() < 5e-3
     if len(d['temp_usage']):
+        # usage = sum of top-k weights / life: one top-k membership flip at a near-tie (fp16 keys vs the fp32
+        # reference trace) moves an entry by ~1/30, so bound the mean tightly and the max loosely
         u = m.temporary_work_mem.get_usage().float().cpu()
-        assert (u - torch.from_numpy(d['temp_usage'])).abs().max().item() < 3e-2
+        du = (u - torch.from_numpy(d['temp_usage'])).abs()
+        assert du.mean().item() < 5e-3 and du.max().item() < 0.1, (du.mean().item(), du.max().item())
     return core
 
 
@@ -81,7 +84,7 @@ def test_two_objects_two_groups(net):
 
 def test_disable_memory_updates_does_not_advance_state(net):
     dev = 'cuda'
-    H, W = 64, 96
+    H, W = 96, 128                                 # 48 memory columns per frame >= top_k
     core = InferenceCore(net, dict(BASE))
     core.set_all_labels([1])
     core.put_to_permanent_memory(synth_frame(0, H, W, structured=True).to(dev), synth_mask(0, H, W, 1).to(dev))

@@ -14,12 +14,12 @@ TOL_SCORE = 2e-4
 TOL_USAGE = 2e-3
 
 
-def _check(case, top_k=30):
+def _check(case, top_k=30, max_ambiguous=None):
     r = k1_ref.compare(case, top_k)
     assert r['score_err'] < TOL_SCORE, r
     assert r['layout_err'] == 0.0, r
     assert r['out_err_clear'] < TOL_OUT, r
-    assert r['ambiguous'] <= max(3, case['hw'] // 50), r
+    assert r['ambiguous'] <= (max_ambiguous if max_ambiguous is not None else max(3, case['hw'] // 50)), r
     assert r['usage_err'] < TOL_USAGE, r
     assert abs(r['usage_sum'] - case['hw']) < 0.05 * case['hw'] + 1, r    # affinity columns sum to 1
     return r
@@ -59,3 +59,16 @@ def test_config2_shape_480p():
     # BASELINE.json config 2 at its largest memory: HW=1620, 5 permanent + 9 working frames, 1 object
     case = k1_ref.make_case(hw=1620, sizes=(0, 9 * 1620, 5 * 1620), n_obj=1, group_begins=[(0, 1, [0, 0, 0])], seed=7)
     _check(case)
+
+
+def test_planted_cluster_overflows_candidate_lists():
+    # 50 memory columns nearly identical to every query sit in two consecutive tiles of ONE column slice, so a single
+    # per-slice candidate list receives more than 32 entries and the in-kernel compaction path must stay exact.
+    import torch
+    case = k1_ref.make_case(hw=1620, sizes=(0, 4096, 0), n_obj=1, group_begins=[(0, 1, [0, 0, 0])], seed=8)
+    g = torch.Generator().manual_seed(80)
+    q0 = torch.randn(64, generator=g) * 0.6
+    case['qk'] = (q0[None, :] + 0.02 * torch.randn(1620, 64, generator=g)).half()
+    planted = list(range(128, 160)) + list(range(192, 210))
+    case['banks'][1]['key'][planted] = (q0[None, :] + 0.05 * torch.randn(len(planted), 64, generator=g)).half()
+    _check(case, max_ambiguous=400)     # near-identical planted columns produce near-ties at rank 30 by construction

@@ -93,3 +93,9 @@ extern "C" int xm_debug_last_trap(int* out) {
     for (int i = 0; i < 7; ++i) out[i] = g_trap_host[i];
     return g_trap_host[0];
 }
+
+// ---- launch accounting (bench.py reports how many of this library's kernels ran in the timed region) ----
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void xm_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long xm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -30,3 +30,5 @@ int xm_make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_
                      const uint64_t* strides_bytes, const uint32_t* box);
 
 int xm_num_sms();
+
+void xm_count_launches(int n);

@@ -24,7 +24,6 @@ using namespace tc5;
 
 namespace {
 
-constexpr int CONV_STAGES = 3;
 
 struct alignas(64) ConvMaps {
     CUtensorMap a[3];
@@ -48,9 +47,12 @@ struct ConvP {
     __half* out;
     __half* out_relu;
     int out_stride, out_offset;
+    int splits, ksteps_per_split;     // split-K: blockIdx.z owns k-steps [z*kps, min((z+1)*kps, ksteps))
+    float* ws_partial;                // [tile][split][128][BN] fp32
+    int* ws_counter;                  // [tile] arrival counters (zero before and after every launch)
 };
 
-template <int BN>
+template <int BN, int CONV_STAGES>
 struct ConvSmem {
     alignas(1024) uint8_t a[CONV_STAGES][128 * 128];
     alignas(1024) uint8_t b[CONV_STAGES][BN * 128];
@@ -58,13 +60,15 @@ struct ConvSmem {
     uint64_t empty[CONV_STAGES];
     uint64_t done;
     uint32_t tmem_base;
+    int is_last;
 };
 
-template <int BN>
+template <int BN, int CONV_STAGES>
 __global__ void __launch_bounds__(192)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
     extern __shared__ uint8_t smem_raw[];
-    ConvSmem<BN>& sm = *reinterpret_cast<ConvSmem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    using Smem = ConvSmem<BN, CONV_STAGES>;
+    Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     int tile = blockIdx.x;
@@ -77,7 +81,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
     const int taps = p.ksize * p.ksize;
     int cb_total = 0;
     for (int s = 0; s < p.n_src; ++s) cb_total += p.cblocks[s];
-    const int ksteps = taps * cb_total;
+    const int ksteps_all = taps * cb_total;
+    const int k_begin = blockIdx.z * p.ksteps_per_split;
+    const int k_end = min(ksteps_all, k_begin + p.ksteps_per_split);
+    const int ksteps = k_end - k_begin;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < CONV_STAGES; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
@@ -92,27 +99,28 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
 
     if (warp == 0) {
         if (lane == 0) {
-            int it = 0;
-            for (int tap = 0; tap < taps; ++tap) {
+            for (int it = 0; it < ksteps; ++it) {
+                const int kk = k_begin + it;
+                const int tap = kk / cb_total;
+                int cb = kk - tap * cb_total;
+                int s = 0;
+                if (p.n_src > 1 && cb >= p.cblocks[0]) { cb -= p.cblocks[0]; s = 1; }
+                if (p.n_src > 2 && s == 1 && cb >= p.cblocks[1]) { cb -= p.cblocks[1]; s = 2; }
                 const int kh = tap / p.ksize, kw = tap % p.ksize;
-                for (int s = 0; s < p.n_src; ++s) {
-                    const int bb = p.bcast[s] ? 0 : b;
-                    for (int cb = 0; cb < p.cblocks[s]; ++cb, ++it) {
-                        const int st = it % CONV_STAGES, ph = (it / CONV_STAGES) & 1;
-                        mbar_wait(&sm.empty[st], ph ^ 1, 21);
-                        mbar_expect_tx(&sm.full[st], 128 * 128 + BN * 128);
-                        if (p.stride == 1) {
-                            tma_load_4d(sm.a[st], &maps.a[s], &sm.full[st], cb * 64, x0 + kw - p.pad, y0 + kh - p.pad, bb);
-                        } else {
-                            // input pixel (2*yo + kh - pad, 2*xo + kw - pad) -> parity plane + half coordinate
-                            const int dy = kh - p.pad, dx = kw - p.pad;
-                            const int py = dy & 1, px = dx & 1;
-                            const int hy = (dy - py) / 2, hx = (dx - px) / 2;
-                            tma_load_5d(sm.a[st], &maps.a[s], &sm.full[st], cb * 64, px, x0 + hx, py, y0 + hy);
-                        }
-                        tma_load_2d(sm.b[st], &maps.w, &sm.full[st], tap * p.cin_total + p.choff[s] + cb * 64, n0);
-                    }
+                const int bb = p.bcast[s] ? 0 : b;
+                const int st = it % CONV_STAGES, ph = (it / CONV_STAGES) & 1;
+                mbar_wait(&sm.empty[st], ph ^ 1, 21);
+                mbar_expect_tx(&sm.full[st], 128 * 128 + BN * 128);
+                if (p.stride == 1) {
+                    tma_load_4d(sm.a[st], &maps.a[s], &sm.full[st], cb * 64, x0 + kw - p.pad, y0 + kh - p.pad, bb);
+                } else {
+                    // input pixel (2*yo + kh - pad, 2*xo + kw - pad) -> parity plane + half coordinate
+                    const int dy = kh - p.pad, dx = kw - p.pad;
+                    const int py = dy & 1, px = dx & 1;
+                    const int hy = (dy - py) / 2, hx = (dx - px) / 2;
+                    tma_load_5d(sm.a[st], &maps.a[s], &sm.full[st], cb * 64, px, x0 + hx, py, y0 + hy);
                 }
+                tma_load_2d(sm.b[st], &maps.w, &sm.full[st], tap * p.cin_total + p.choff[s] + cb * 64, n0);
             }
         }
     } else if (warp == 1) {
@@ -141,18 +149,57 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
         const size_t rpix = ((size_t)(p.residual_bcast ? 0 : b) * p.Ho + yo) * p.Wo + xo;
         mbar_wait(&sm.done, 0, 23);
         tc_fence_after();
+        const int tile_lin = blockIdx.x * gridDim.y + blockIdx.y;
+        if (p.splits > 1) {
+            // write this split's fp32 partial tile, then the last CTA to arrive reduces all splits in fixed order
+            float* mine = p.ws_partial + (((size_t)tile_lin * p.splits + blockIdx.z) * 128 + row) * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(lane_base) << 16) + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(mine + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) {
+                const int old = atomicAdd(p.ws_counter + tile_lin, 1);
+                sm.is_last = (old == p.splits - 1) ? 1 : 0;
+                if (old == p.splits - 1) p.ws_counter[tile_lin] = 0;      // ready for the next launch
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (!sm.is_last) goto teardown;
+            __threadfence();
+        }
         const bool vec_ok = (p.out_stride % 8 == 0) && (p.out_offset % 8 == 0) && (p.residual_stride % 8 == 0);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(lane_base) << 16) + c0, r);
-            tmem_ld_wait();
+            float acc[32];
+            if (p.splits > 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+                for (int z = 0; z < p.splits; ++z) {
+                    const float* src = p.ws_partial + (((size_t)tile_lin * p.splits + z) * 128 + row) * BN + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 f = __ldcg(reinterpret_cast<const float4*>(src + j));
+                        acc[j] += f.x; acc[j + 1] += f.y; acc[j + 2] += f.z; acc[j + 3] += f.w;
+                    }
+                }
+            } else {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(lane_base) << 16) + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+            }
             const int n = n0 + c0;
             if (!pix_ok || n >= p.cout) continue;
             const bool full = (n + 32 <= p.cout) && vec_ok;
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + ((n + j < p.cout) ? __ldg(p.bias + n + j) : 0.f);
+            for (int j = 0; j < 32; ++j) v[j] = acc[j] + ((n + j < p.cout) ? __ldg(p.bias + n + j) : 0.f);
             if (p.residual) {
                 const __half* rp = p.residual + rpix * p.residual_stride + n;
                 if (full) {
@@ -204,22 +251,24 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
             }
         }
     }
+teardown:
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, BN);
 }
 
-template <int BN>
+template <int BN, int STAGES>
 int launch_conv(const ConvMaps& maps, const ConvP& p, int cout_pad, cudaStream_t stream) {
     tc5_debug_init();
     static bool attr_done = false;
-    const int smem = (int)sizeof(ConvSmem<BN>) + 1024;
+    const int smem = (int)sizeof(ConvSmem<BN, STAGES>) + 1024;
     if (!attr_done) {
-        XM_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        XM_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    dim3 grid(p.tiles_x * p.tiles_y * p.batch, cout_pad / BN);
-    conv_igemm_kernel<BN><<<grid, 192, smem, stream>>>(maps, p);
+    dim3 grid(p.tiles_x * p.tiles_y * p.batch, cout_pad / BN, p.splits);
+    conv_igemm_kernel<BN, STAGES><<<grid, 192, smem, stream>>>(maps, p);
+    xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
 }
@@ -292,5 +341,26 @@ extern "C" int xm_conv2d_nhwc(const xm_conv_args_t* a, void* stream_) {
         uint32_t bx[2] = {64, (uint32_t)BN};
         if (xm_make_tmap_f16(&maps.w, a->weight, 2, d, st, bx)) return XM_ERR_CUDA;
     }
-    return BN == 128 ? launch_conv<128>(maps, p, a->cout_pad, stream) : launch_conv<64>(maps, p, a->cout_pad, stream);
+    // occupancy plan: many CTAs -> 3 stages (2 CTAs/SM overlap prologue/epilogue); few CTAs -> 6 stages (hide L2
+    // latency in the k-loop) and split-K over blockIdx.z so that idle SMs share the reduction.
+    int cb_total = 0;
+    for (int s = 0; s < p.n_src; ++s) cb_total += p.cblocks[s];
+    const int ksteps = a->ksize * a->ksize * cb_total;
+    const int ctas = p.tiles_x * p.tiles_y * p.batch * (a->cout_pad / BN);
+    const int sms = xm_num_sms();
+    p.splits = 1;
+    if (a->workspace && ctas * 2 <= sms) {
+        int s = sms / ctas;
+        if (s > ksteps / 8) s = ksteps / 8;
+        if (s > 8) s = 8;
+        const int64_t need = 65536 * 4 + (int64_t)ctas * s * 128 * BN * 4;
+        if (s >= 2 && need <= a->workspace_bytes && ctas <= 65536) p.splits = s;
+    }
+    p.ksteps_per_split = (ksteps + p.splits - 1) / p.splits;
+    p.splits = (ksteps + p.ksteps_per_split - 1) / p.ksteps_per_split;
+    p.ws_counter = (int*)a->workspace;
+    p.ws_partial = a->workspace ? (float*)((char*)a->workspace + 65536 * 4) : nullptr;
+    const bool deep = ctas < 2 * sms;
+    if (BN == 128) return deep ? launch_conv<128, 6>(maps, p, a->cout_pad, stream) : launch_conv<128, 3>(maps, p, a->cout_pad, stream);
+    return deep ? launch_conv<64, 6>(maps, p, a->cout_pad, stream) : launch_conv<64, 3>(maps, p, a->cout_pad, stream);
 }

@@ -132,12 +132,15 @@ __global__ void keyproj_post_kernel(const __half* __restrict__ proj, int pstride
 }
 
 // ---------------------------------------------------------------- CBAM
-// (a) per-(image, channel) mean and max over all pixels.  grid (C/64, B), block (64, 4)
-__global__ void cbam_pool_kernel(const __half* __restrict__ x, int HW, int C, float* __restrict__ avg, float* __restrict__ mx) {
+// (a) per-(image, channel) partial sum and max over a slice of the pixels.  grid (C/64, B, CBAM_SLICES), block (64, 4)
+constexpr int CBAM_SLICES = 16;
+__global__ void cbam_pool_kernel(const __half* __restrict__ x, int HW, int C, float* __restrict__ psum, float* __restrict__ pmax) {
     __shared__ float ssum[4][64], smax[4][64];
-    const int c = blockIdx.x * 64 + threadIdx.x, b = blockIdx.y;
+    const int c = blockIdx.x * 64 + threadIdx.x, b = blockIdx.y, sl = blockIdx.z;
+    const int per = (HW + CBAM_SLICES - 1) / CBAM_SLICES;
+    const int p0 = sl * per, p1 = min(HW, p0 + per);
     float s = 0.f, m = -INFINITY;
-    for (int p = threadIdx.y; p < HW; p += 4) {
+    for (int p = p0 + threadIdx.y; p < p1; p += 4) {
         const float v = __half2float(x[((size_t)b * HW + p) * C + c]);
         s += v; m = fmaxf(m, v);
     }
@@ -145,24 +148,35 @@ __global__ void cbam_pool_kernel(const __half* __restrict__ x, int HW, int C, fl
     __syncthreads();
     if (threadIdx.y == 0) {
         for (int i = 1; i < 4; ++i) { s += ssum[i][threadIdx.x]; m = fmaxf(m, smax[i][threadIdx.x]); }
-        avg[(size_t)b * C + c] = s / HW;
-        mx[(size_t)b * C + c] = m;
+        psum[((size_t)b * CBAM_SLICES + sl) * C + c] = s;
+        pmax[((size_t)b * CBAM_SLICES + sl) * C + c] = m;
     }
 }
 // (b) scale_c = sigmoid(mlp(avg) + mlp(max)).  One block (C threads) per image; hidden width R = C/16.
-__global__ void cbam_mlp_kernel(const float* __restrict__ avg, const float* __restrict__ mx, const float* __restrict__ w1,
+__global__ void cbam_mlp_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, int HW, const float* __restrict__ w1,
                                 const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int C,
                                 int R, float* __restrict__ scale) {
     extern __shared__ float sh[];          // [2][C] inputs, [2][R] hidden
     float* in0 = sh; float* in1 = sh + C; float* h0 = sh + 2 * C; float* h1 = h0 + R;
     const int b = blockIdx.x, t = threadIdx.x;
-    in0[t] = avg[(size_t)b * C + t]; in1[t] = mx[(size_t)b * C + t];
+    {
+        float s = 0.f, m = -INFINITY;
+        for (int sl = 0; sl < CBAM_SLICES; ++sl) {
+            s += psum[((size_t)b * CBAM_SLICES + sl) * C + t];
+            m = fmaxf(m, pmax[((size_t)b * CBAM_SLICES + sl) * C + t]);
+        }
+        in0[t] = s / HW; in1[t] = m;
+    }
     __syncthreads();
-    if (t < 2 * R) {
-        const int r = t % R; const float* in = (t < R) ? in0 : in1;
-        float a = b1[r];
-        for (int c = 0; c < C; ++c) a += w1[(size_t)r * C + c] * in[c];
-        (t < R ? h0 : h1)[r] = fmaxf(a, 0.f);
+    // hidden layer: one warp per (input, unit) pair, lanes stride over C
+    const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
+    for (int u = warp; u < 2 * R; u += nwarps) {
+        const int r = u % R; const float* in = (u < R) ? in0 : in1;
+        float a = 0.f;
+        for (int c = lane; c < C; c += 32) a += w1[(size_t)r * C + c] * in[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) (u < R ? h0 : h1)[r] = fmaxf(a + b1[r], 0.f);
     }
     __syncthreads();
     float a = 2.f * b2[t];
@@ -352,6 +366,7 @@ extern "C" int xm_im2col_stem(const float* image, const float* masks, int32_t n,
     XM_REQUIRE(kpad >= 49 * C && kpad % 64 == 0, "xm_im2col_stem: kpad must be a multiple of 64 >= %d", 49 * C);
     const size_t total = (size_t)n * (H / 2) * (W / 2) * kpad;
     im2col_stem_kernel<<<grid_for(total), 256, 0, STREAM>>>(image, masks, n, H, W, C, kpad, (__half*)out);
+    xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
 }
@@ -360,6 +375,7 @@ extern "C" int xm_maxpool3x3s2(const void* in, int32_t B, int32_t H, int32_t W, 
     XM_REQUIRE(in && out && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "xm_maxpool3x3s2: bad arguments");
     const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
     maxpool_kernel<<<grid_for(total), 256, 0, STREAM>>>((const __half*)in, B, H, W, C, relu, (__half*)out);
+    xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
 }
@@ -367,6 +383,7 @@ extern "C" int xm_maxpool3x3s2(const void* in, int32_t B, int32_t H, int32_t W, 
 extern "C" int xm_relu(const void* in, void* out, int64_t n, void* stream) {
     XM_REQUIRE(in && out && n % 8 == 0, "xm_relu: n must be a multiple of 8");
     relu_kernel<<<grid_for(n / 8), 256, 0, STREAM>>>((const uint4*)in, (uint4*)out, (size_t)n / 8);
+    xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
 }
@@ -377,22 +394,25 @@ extern "C" int xm_keyproj_post(const void* proj, int32_t pstride, int32_t hw, in
     const int rows = qp ? hw_pad : hw;
     keyproj_post_kernel<<<(rows + 7) / 8, 256, 0, STREAM>>>((const __half*)proj, pstride, hw, rows, (__half*)key, (__half*)sel, shr,
                                                             (__half*)qp, bsq);
+    xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
 }
 
 extern "C" int xm_cbam(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, const float* w1, const float* b1, const float* w2,
                        const float* b2, const float* w7, float b7, float* scratch, void* out, void* out_relu, void* stream) {
-    // scratch: avg[B*C] | max[B*C] | scale[B*C] | comp[B*H*W*2]  floats
+    // scratch: psum[B*16*C] | pmax[B*16*C] | scale[B*C] | comp[B*H*W*2]  floats
     XM_REQUIRE(x && out && scratch && C % 64 == 0 && C <= 1024, "xm_cbam: bad arguments");
     const int HW = H * W, R = C / 16;
-    float* avg = scratch; float* mx = avg + (size_t)B * C; float* scale = mx + (size_t)B * C; float* comp = scale + (size_t)B * C;
-    cbam_pool_kernel<<<dim3(C / 64, B), dim3(64, 4), 0, STREAM>>>((const __half*)x, HW, C, avg, mx);
-    cbam_mlp_kernel<<<B, C, (2 * C + 2 * R) * sizeof(float), STREAM>>>(avg, mx, w1, b1, w2, b2, C, R, scale);
+    float* avg = scratch; float* mx = avg + (size_t)B * CBAM_SLICES * C; float* scale = mx + (size_t)B * CBAM_SLICES * C;
+    float* comp = scale + (size_t)B * C;
+    cbam_pool_kernel<<<dim3(C / 64, B, CBAM_SLICES), dim3(64, 4), 0, STREAM>>>((const __half*)x, HW, C, avg, mx);
+    cbam_mlp_kernel<<<B, C, (2 * C + 2 * R) * sizeof(float), STREAM>>>(avg, mx, HW, w1, b1, w2, b2, C, R, scale);
     const size_t npix = (size_t)B * HW;
     cbam_spatial_pool_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, STREAM>>>((const __half*)x, scale, B, HW, C, comp);
     cbam_apply_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, STREAM>>>((const __half*)x, scale, comp, w7, b7, B, H, W, C, (__half*)out,
                                                                      (__half*)out_relu);
+    xm_count_launches(3);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
 }
@@ -403,6 +423,7 @@ extern "C" int xm_upsample2x_add(const void* g, const void* skip, int32_t B, int
     const size_t total = (size_t)B * 4 * h * w * (C / 2);
     upsample2x_add_kernel<<<grid_for(total), 256, 0, STREAM>>>((const __half*)g, (const __half*)skip, B, h, w, C, (__half*)out,
                                                                (__half*)out_relu);
+    xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
 }
@@ -412,6 +433,7 @@ extern "C" int xm_area_down(const void* in, const void* extra, int32_t B, int32_
     XM_REQUIRE(in && out && f >= 1 && H % f == 0 && W % f == 0 && cpad >= C + (extra ? 1 : 0), "xm_area_down: bad arguments");
     const size_t total = (size_t)B * (H / f) * (W / f) * cpad;
     area_down_kernel<<<grid_for(total), 256, 0, STREAM>>>((const __half*)in, (const __half*)extra, B, H, W, C, f, cpad, (__half*)out);
+    xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
 }
@@ -420,6 +442,7 @@ extern "C" int xm_gru(const void* values, const float* h, int64_t npix, int32_t 
     XM_REQUIRE(values && h && h_out && h_out16 && npix > 0, "xm_gru: bad arguments");
     gru_kernel<<<grid_for((size_t)npix * hidden_dim), 256, 0, STREAM>>>((const __half*)values, h, (size_t)npix, hidden_dim, h_out,
                                                                       (__half*)h_out16);
+    xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
 }
@@ -427,6 +450,7 @@ extern "C" int xm_gru(const void* values, const float* h, int64_t npix, int32_t 
 extern "C" int xm_upsample4x_aggregate(const void* logits4, int32_t n, int32_t h4, int32_t w4, float* prob, float* logits, void* stream) {
     XM_REQUIRE(logits4 && prob && n >= 1 && n <= XM_MAX_GROUPS * 4, "xm_upsample4x_aggregate: bad arguments");
     upsample4x_aggregate_kernel<<<grid_for((size_t)16 * h4 * w4), 256, 0, STREAM>>>((const __half*)logits4, n, h4, w4, prob, logits);
+    xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
 }
@@ -435,6 +459,7 @@ extern "C" int xm_value_append(const void* value_hwc, int32_t n_obj, int32_t hw,
     XM_REQUIRE(value_hwc && arena && n_obj >= 1 && hw > 0 && col0 >= 0 && col0 + hw <= cap, "xm_value_append: bad arguments");
     value_append_kernel<<<dim3((hw + 31) / 32, XM_CV / 32, n_obj), dim3(32, 8), 0, STREAM>>>((const __half*)value_hwc, hw, (int)cap, col0,
                                                                                            (__half*)arena);
+    xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
 }

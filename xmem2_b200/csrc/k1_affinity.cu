@@ -117,23 +117,41 @@ __global__ void key_pack_kernel(const __half* __restrict__ key, int n, __half* _
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 1: per-slice top-k candidates
+// scan kernel (two modes) : streams S tiles and keeps, per query, a 32-entry summary of each column slice
+//   MODE_SLOTMAX : slot[j] = max over the slice's tiles of S[q, 64*t + j]  -> 32 running maxima of disjoint
+//                  column subsets, branch-free (one FMNMX per score).  The k-th largest of all slot maxima is a
+//                  LOWER bound tau_lo of the true k-th largest score (they are distinct memory columns) and in
+//                  practice within a few ranks of it.
+//   MODE_COLLECT : keeps the 32 largest scores > pred(tau_lo) of the slice (append until full, then
+//                  replace-min) -> exact, and 99.7 % of the scores fail the first compare.
+// Threads: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = 8 selection warps; the warp pair
+// (w, w+4) shares a TMEM lane quadrant and splits the 64 tile columns in halves.
 // ---------------------------------------------------------------------------------------------
-struct P1Smem {
+constexpr int MODE_SLOTMAX = 0;
+constexpr int MODE_COLLECT = 1;
+constexpr int SCAN_THREADS = 64 + 256;
+
+struct ScanSmem {
     alignas(1024) uint8_t q[2][TQ * 128];                 // 2 K-halves x (128 rows x 128 B)
     alignas(1024) uint8_t k[P1_STAGES][2][TN * 128];      // per stage 2 K-halves x (64 rows x 128 B)
-    float list[LISTK][TQ];
+    float list[2][2 * LISTK][TQ];                         // MODE_COLLECT: per (column half, query) append list (2x capacity)
     alignas(8) uint64_t qfull;
     uint64_t kfull[P1_STAGES], kempty[P1_STAGES];
     uint64_t sfull[P1_SBUF], sempty[P1_SBUF];
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(192, 1)
-k1_topk_pass1(const __grid_constant__ K1Maps maps, const K1Seg sg, const float* __restrict__ bsq, int hw, int hw_pad,
-              int top_k, int tiles_per_split, float* __restrict__ cand, float* __restrict__ dbg_scores) {
+__device__ __forceinline__ float score2(uint32_t acc_bits, float bsq8, float ms) {
+    // ((S' - b_sq) * shrinkage) / 8 == (S'/8 - b_sq/8) * shrinkage exactly (power-of-two scaling commutes with rounding)
+    return fmaf(__uint_as_float(acc_bits), 0.125f, -bsq8) * ms;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(SCAN_THREADS, 1)
+k1_scan(const __grid_constant__ K1Maps maps, const K1Seg sg, const float* __restrict__ bsq, const float* __restrict__ tau_lo,
+        int hw_pad, int tiles_per_split, float* __restrict__ cand, float* __restrict__ dbg_scores) {
     extern __shared__ uint8_t smem_raw[];
-    P1Smem& sm = *reinterpret_cast<P1Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    ScanSmem& sm = *reinterpret_cast<ScanSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x, split = blockIdx.y;
     const int total_tiles = sg.tile0[sg.nseg];
@@ -144,7 +162,7 @@ k1_topk_pass1(const __grid_constant__ K1Maps maps, const K1Seg sg, const float* 
     if (threadIdx.x == 0) {
         mbar_init(&sm.qfull, 1);
         for (int i = 0; i < P1_STAGES; ++i) { mbar_init(&sm.kfull[i], 1); mbar_init(&sm.kempty[i], 1); }
-        for (int i = 0; i < P1_SBUF; ++i) { mbar_init(&sm.sfull[i], 1); mbar_init(&sm.sempty[i], 128); }
+        for (int i = 0; i < P1_SBUF; ++i) { mbar_init(&sm.sfull[i], 1); mbar_init(&sm.sempty[i], 256); }
         fence_mbar_init();
     }
     if (warp == 1) { tmem_alloc(&sm.tmem_base, 256); tmem_relinquish(); }
@@ -193,71 +211,127 @@ k1_topk_pass1(const __grid_constant__ K1Maps maps, const K1Seg sg, const float* 
             }
         }
     } else {
-        // selection warps: one thread per query (TMEM lane)
         const int lane_base = (warp & 3) * 32;
+        const int half = (warp - 2) >> 2;               // which 32 of the tile's 64 columns
         const int row = lane_base + lane;
         const int q = qtile * TQ + row;
-        const float my_bsq = bsq[q];            // bsq is padded to hw_pad
-        for (int i = 0; i < LISTK; ++i) sm.list[i][row] = -INFINITY;
-        float cur_min = -INFINITY;
-        int cur_pos = 0;
+        const float bsq8 = bsq[q] * 0.125f;
+        float slot[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) slot[j] = -INFINITY;
+        // MODE_COLLECT state: append-only list of capacity 2*LISTK, compacted to the LISTK largest when it could overflow
+        float thr = -INFINITY;
+        int count = 0;
+        float* mylist = &sm.list[half][0][row];          // element u at mylist[u * TQ]
+        if (MODE == MODE_COLLECT) {
+            const float t = tau_lo[q];
+            thr = (t == -INFINITY) ? -INFINITY : ((t == INFINITY) ? FLT_MAX : __uint_as_float(
+                      t > 0.f ? __float_as_uint(t) - 1u : (t < 0.f ? __float_as_uint(t) + 1u : 0x80000001u)));   // pred(tau_lo)
+        }
+        auto compact = [&]() {      // keep the LISTK largest of `count` entries; thr = the smallest kept (rare path)
+            for (int keep = 0; keep < LISTK; ++keep) {
+                float m = mylist[keep * TQ]; int p = keep;
+                for (int u = keep + 1; u < count; ++u) { const float v = mylist[u * TQ]; if (v > m) { m = v; p = u; } }
+                const float t0 = mylist[keep * TQ]; mylist[keep * TQ] = m; mylist[p * TQ] = t0;
+            }
+            count = LISTK;
+            thr = mylist[(LISTK - 1) * TQ];
+        };
+        // software prefetch of the shrinkage values of the next tile (hides the L2 latency behind this tile's work)
+        float ms_next[32];
+        auto load_ms = [&](int i, float (&ms)[32]) {
+            int s, col, lo, nv;
+            locate_tile(sg, t_begin + i, s, col, lo, nv);
+            const int c0 = col + half * 32;
+            const int jlo = lo - half * 32, jhi = nv - half * 32;
+            const float* shr = sg.shr[s] + c0;
+            if (jlo <= 0 && jhi >= 32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 f = __ldg(reinterpret_cast<const float4*>(shr + j));   // c0 is a multiple of 8
+                    ms[j] = f.x; ms[j + 1] = f.y; ms[j + 2] = f.z; ms[j + 3] = f.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ms[j] = (j >= jlo && j < jhi) ? __ldg(shr + j) : 1.f;
+            }
+        };
+        if (nt > 0) load_ms(0, ms_next);
         for (int i = 0; i < nt; ++i) {
             int s, col, lo, nv;
             locate_tile(sg, t_begin + i, s, col, lo, nv);
+            float ms[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ms[j] = ms_next[j];
+            if (i + 1 < nt) load_ms(i + 1, ms_next);
             const int sb = i % P1_SBUF, sph = (i / P1_SBUF) & 1;
             mbar_wait(&sm.sfull[sb], sph, 5);
             tc_fence_after();
-            uint32_t r0[32], r1[32];
-            const uint32_t taddr = tmem + (static_cast<uint32_t>(lane_base) << 16) + sb * TN;
-            tmem_ld_32x32b_x32(taddr, r0);
-            tmem_ld_32x32b_x32(taddr + 32, r1);
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(lane_base) << 16) + sb * TN + half * 32, r);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&sm.sempty[sb]);
-            const float* shr = sg.shr[s] + col;
-            float* dbg = dbg_scores ? dbg_scores + ((ptrdiff_t)sg.col0[s] + (col - sg.begin[s])) * (ptrdiff_t)hw_pad + q : nullptr;
+            const int c0 = col + half * 32;                  // first column of this thread's 32
+            const int jlo = lo - half * 32, jhi = nv - half * 32;   // valid j in [jlo, jhi)
+            const bool full_tile = (jlo <= 0) && (jhi >= 32);
+            float sc[32];
+            if (full_tile) {
 #pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                const bool valid = (j >= lo) && (j < nv);
-                const float ms = valid ? __ldg(shr + j) : 1.f;
-                float sc = score(j < 32 ? r0[j & 31] : r1[j & 31], my_bsq, ms);
-                if (!valid) sc = -INFINITY;
-                if (dbg && valid) dbg[(ptrdiff_t)j * hw_pad] = sc;
-                if (sc > cur_min) {
-                    sm.list[cur_pos][row] = sc;
-                    float m = sm.list[0][row];
-                    int p = 0;
-                    for (int u = 1; u < top_k; ++u) {
-                        float v = sm.list[u][row];
-                        if (v < m) { m = v; p = u; }
-                    }
-                    cur_min = m;
-                    cur_pos = p;
+                for (int j = 0; j < 32; ++j) sc[j] = score2(r[j], bsq8, ms[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sc[j] = (j >= jlo && j < jhi) ? score2(r[j], bsq8, ms[j]) : -INFINITY;
+            }
+            if (MODE == MODE_SLOTMAX) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) slot[j] = fmaxf(slot[j], sc[j]);
+                if (dbg_scores) {        // tests only (warp-uniform)
+                    float* dbg = dbg_scores + ((ptrdiff_t)sg.col0[s] + (c0 - sg.begin[s])) * (ptrdiff_t)hw_pad + q;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (sc[j] != -INFINITY) dbg[(ptrdiff_t)j * hw_pad] = sc[j];
                 }
+            } else {
+                if (count > LISTK) compact();                 // guarantees room for 32 appends below
+                float* wp = mylist + count * TQ;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {                // branch-free predicated append
+                    const bool take = sc[j] > thr;
+                    if (take) *wp = sc[j];
+                    wp += take ? TQ : 0;
+                }
+                count = static_cast<int>(wp - mylist) / TQ;
             }
         }
-        float* dst = cand + ((size_t)split * hw_pad + q) * LISTK;
-        for (int u = 0; u < LISTK; ++u) dst[u] = (u < top_k) ? sm.list[u][row] : -INFINITY;
+        float* dst = cand + ((size_t)(split * 2 + half) * hw_pad + q) * LISTK;
+        if (MODE == MODE_SLOTMAX) {
+#pragma unroll
+            for (int u = 0; u < LISTK; u += 4) *reinterpret_cast<float4*>(dst + u) = make_float4(slot[u], slot[u + 1], slot[u + 2], slot[u + 3]);
+        } else {
+            if (count > LISTK) compact();
+            for (int u = 0; u < LISTK; ++u) dst[u] = (u < count) ? mylist[u * TQ] : -INFINITY;
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
-// merge the per-slice candidate lists: one warp per query, lane l owns slice l (nsplit <= 32)
-__global__ void k1_topk_merge(const float* __restrict__ cand, int nsplit, int hw, int hw_pad, int top_k,
+// k-th largest over the per-slice 32-entry lists: one warp per query, lane l owns list l (nlists <= 32).
+// want_den: also 1 / sum_topk exp(S)  (do_softmax top-k branch, memory_util.py:48-49: no max subtraction)
+__global__ void k1_topk_merge(const float* __restrict__ cand, int nlists, int hw, int hw_pad, int top_k, int want_den,
                               float* __restrict__ tau, float* __restrict__ inv_den) {
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (q >= hw_pad) return;
     if (q >= hw) {                       // padded query rows never select anything
-        if (lane == 0) { tau[q] = INFINITY; inv_den[q] = 0.f; }
+        if (lane == 0) { tau[q] = INFINITY; if (want_den) inv_den[q] = 0.f; }
         return;
     }
     float v[LISTK];
 #pragma unroll
     for (int u = 0; u < LISTK; ++u) v[u] = -INFINITY;
-    if (lane < nsplit) {
+    if (lane < nlists) {
         const float4* src = reinterpret_cast<const float4*>(cand + ((size_t)lane * hw_pad + q) * LISTK);
 #pragma unroll
         for (int u = 0; u < LISTK / 4; ++u) {
@@ -267,23 +341,30 @@ __global__ void k1_topk_merge(const float* __restrict__ cand, int nsplit, int hw
     }
     float den = 0.f, kth = -INFINITY;
     for (int r = 0; r < top_k; ++r) {
-        float m = v[0];
+        float t16[16], t8[8], t4[4];
 #pragma unroll
-        for (int u = 1; u < LISTK; ++u) m = fmaxf(m, v[u]);
+        for (int u = 0; u < 16; ++u) t16[u] = fmaxf(v[u], v[u + 16]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t8[u] = fmaxf(t16[u], t16[u + 8]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) t4[u] = fmaxf(t8[u], t8[u + 4]);
+        const float m = fmaxf(fmaxf(t4[0], t4[2]), fmaxf(t4[1], t4[3]));
         float g = m;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, o));
         const unsigned owners = __ballot_sync(0xffffffffu, m == g);
-        if (lane == __ffs(owners) - 1) {
-            bool done = false;
+        if (lane == __ffs(owners) - 1) {         // remove ONE instance of the maximum from its owner
+            unsigned eq = 0u;
 #pragma unroll
-            for (int u = 0; u < LISTK; ++u)
-                if (!done && v[u] == g) { v[u] = -INFINITY; done = true; }
+            for (int u = 0; u < LISTK; ++u) eq |= (v[u] == g ? 1u : 0u) << u;
+            const int first = __ffs(eq) - 1;
+#pragma unroll
+            for (int u = 0; u < LISTK; ++u) v[u] = (u == first) ? -INFINITY : v[u];
         }
         den += fast_exp(g);
         kth = g;
     }
-    if (lane == 0) { tau[q] = kth; inv_den[q] = 1.f / den; }
+    if (lane == 0) { tau[q] = kth; if (want_den) inv_den[q] = 1.f / den; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -303,7 +384,7 @@ struct P2Smem {
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(SCAN_THREADS, 1)
 k1_readout_pass2(const __grid_constant__ K1Maps maps, const K1Seg sg, const float* __restrict__ bsq,
                  const float* __restrict__ tau, const float* __restrict__ inv_den, int hw_pad, int obj_begin,
                  int n_obj, int tiles_per_split, int do_usage, float* __restrict__ partial) {
@@ -322,8 +403,8 @@ k1_readout_pass2(const __grid_constant__ K1Maps maps, const K1Seg sg, const floa
         mbar_init(&sm.qfull, 1);
         for (int i = 0; i < P2_KSTAGES; ++i) { mbar_init(&sm.kfull[i], 1); mbar_init(&sm.kempty[i], 1); }
         for (int i = 0; i < P2_VSTAGES; ++i) { mbar_init(&sm.vfull[i], 1); mbar_init(&sm.vempty[i], 1); }
-        for (int i = 0; i < P2_SBUF; ++i) { mbar_init(&sm.sfull[i], 1); mbar_init(&sm.sempty[i], 128); }
-        for (int i = 0; i < P2_PBUF; ++i) { mbar_init(&sm.pfull[i], 128); mbar_init(&sm.pempty[i], 1); }
+        for (int i = 0; i < P2_SBUF; ++i) { mbar_init(&sm.sfull[i], 1); mbar_init(&sm.sempty[i], 256); }
+        for (int i = 0; i < P2_PBUF; ++i) { mbar_init(&sm.pfull[i], 256); mbar_init(&sm.pempty[i], 1); }
         mbar_init(&sm.ofull, 1);
         fence_mbar_init();
     }
@@ -405,64 +486,85 @@ k1_readout_pass2(const __grid_constant__ K1Maps maps, const K1Seg sg, const floa
         }
     } else {
         const int lane_base = (warp & 3) * 32;
+        const int half = (warp - 2) >> 2;
         const int row = lane_base + lane;
         const int q = qtile * TQ + row;
-        const float my_bsq = bsq[q];
+        const float bsq8 = bsq[q] * 0.125f;
         const float my_tau = tau[q];
         const float my_inv = inv_den[q];
         const bool usage_cta = do_usage && blockIdx.y == 0;
+        float ms_next[32];
+        auto load_ms = [&](int i, float (&ms)[32]) {
+            int s, col, lo, nv;
+            locate_tile(sg, t_begin + i, s, col, lo, nv);
+            const int c0 = col + half * 32;
+            const int jlo = lo - half * 32, jhi = nv - half * 32;
+            const float* shr = sg.shr[s] + c0;
+            if (jlo <= 0 && jhi >= 32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 f = __ldg(reinterpret_cast<const float4*>(shr + j));
+                    ms[j] = f.x; ms[j + 1] = f.y; ms[j + 2] = f.z; ms[j + 3] = f.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ms[j] = (j >= jlo && j < jhi) ? __ldg(shr + j) : 1.f;
+            }
+        };
+        if (nt > 0) load_ms(0, ms_next);
         for (int i = 0; i < nt; ++i) {
             int s, col, lo, nv;
             locate_tile(sg, t_begin + i, s, col, lo, nv);
+            float ms[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ms[j] = ms_next[j];
+            if (i + 1 < nt) load_ms(i + 1, ms_next);
             const int sb = i % P2_SBUF, sph = (i / P2_SBUF) & 1;
             const int pb = i % P2_PBUF, pph = (i / P2_PBUF) & 1;
             mbar_wait(&sm.sfull[sb], sph, 5);
             tc_fence_after();
-            uint32_t r0[32], r1[32];
-            const uint32_t taddr = tmem_s + (static_cast<uint32_t>(lane_base) << 16) + sb * TN;
-            tmem_ld_32x32b_x32(taddr, r0);
-            tmem_ld_32x32b_x32(taddr + 32, r1);
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_s + (static_cast<uint32_t>(lane_base) << 16) + sb * TN + half * 32, r);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&sm.sempty[sb]);
-            const float* shr = sg.shr[s] + col;
-            float* usage = (usage_cta && sg.usage[s]) ? sg.usage[s] + col : nullptr;
-            uint32_t packed[32];
+            const int c0 = col + half * 32;
+            const int jlo = lo - half * 32, jhi = nv - half * 32;
+            const bool full_tile = (jlo <= 0) && (jhi >= 32);
+            float* usage = (usage_cta && sg.usage[s]) ? sg.usage[s] + c0 : nullptr;
+            // branch-free: p = (S >= tau) ? exp(S) / den : 0   (k of N columns are non-zero)
+            float pv[32];
 #pragma unroll
-            for (int j = 0; j < TN; j += 2) {
-                float pv[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int jj = j + e;
-                    const bool valid = (jj >= lo) && (jj < nv);
-                    const float ms = valid ? __ldg(shr + jj) : 1.f;
-                    const float sc = score(jj < 32 ? r0[jj & 31] : r1[jj & 31], my_bsq, ms);
-                    float p = 0.f;
-                    if (valid && sc >= my_tau) {
-                        p = fast_exp(sc) * my_inv;
-                        if (usage) atomicAdd(usage + jj, p);
-                    }
-                    pv[e] = p;
-                }
-                packed[j >> 1] = pack_half2(pv[0], pv[1]);
+            for (int j = 0; j < 32; ++j) {
+                const float sc = score2(r[j], bsq8, ms[j]);
+                const bool ok = (sc >= my_tau) && (full_tile || (j >= jlo && j < jhi));
+                pv[j] = ok ? fast_exp(sc) * my_inv : 0.f;
             }
+            if (usage) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (pv[j] > 0.f) atomicAdd(usage + j, pv[j]);
+            }
+            uint32_t packed[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) packed[j >> 1] = pack_half2(pv[j], pv[j + 1]);
             mbar_wait(&sm.pempty[pb], pph ^ 1, 9);
             uint8_t* prow = sm.p[pb] + row * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
+                const int chunk = half * 4 + c;
                 uint4 val = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
-                *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = val;
+                *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = val;
             }
             fence_proxy_async_smem();
             mbar_arrive(&sm.pfull[pb]);
         }
-        // epilogue: O^T chunk m, lane = channel, columns = queries
+        // epilogue: warp pair member `half` drains O^T chunk m = half (lane = channel, columns = queries)
         mbar_wait(&sm.ofull, 0, 10);
         tc_fence_after();
         const int n_obj_all = gridDim.y >> 1;
         (void)n_obj;
-#pragma unroll 1
-        for (int m = 0; m < 2; ++m) {
+        {
+            const int m = half;
             const int c = chalf * CHALF + m * 128 + row;
             float* dst = partial + (((size_t)split * n_obj_all + obj) * XM_CV + c) * hw_pad + qtile * TQ;
 #pragma unroll 1
@@ -524,6 +626,7 @@ extern "C" int xm_query_pack(const void* key_hwc, const void* sel_hwc, int32_t h
     const int warps = 8;
     query_pack_kernel<<<(hw_pad + warps - 1) / warps, warps * 32, 0, (cudaStream_t)stream>>>(
         (const __half*)key_hwc, (const __half*)sel_hwc, hw, hw_pad, (__half*)qp, bsq);
+    xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
 }
@@ -533,6 +636,7 @@ extern "C" int xm_key_pack(const void* key_hwc, int32_t n, void* dst_rows, void*
     if (n == 0) return XM_OK;
     const int total = n * XM_CK;
     key_pack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const __half*)key_hwc, n, (__half*)dst_rows);
+    xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
 }
@@ -543,7 +647,7 @@ extern "C" int64_t xm_affinity_workspace_bytes(int32_t hw, int32_t n_obj_total) 
     const int64_t hw_pad = (hw + TQ - 1) / TQ * TQ;
     int64_t b = 0;
     b += align_up((size_t)K1_MAX_SPLIT * hw_pad * LISTK * 4, 256);        // candidates
-    b += 2 * align_up((size_t)hw_pad * 4, 256);                           // tau, inv_den
+    b += 3 * align_up((size_t)hw_pad * 4, 256);                           // tau_lo, tau, inv_den
     b += align_up((size_t)K1_MAX_SPLIT * n_obj_total * XM_CV * hw_pad * 4, 256);   // partial readouts
     return b;
 }
@@ -563,7 +667,8 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
     tc5_debug_init();
     static bool attr_done = false;
     if (!attr_done) {
-        XM_CHECK_CUDA(cudaFuncSetAttribute(k1_topk_pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P1Smem) + 1024));
+        XM_CHECK_CUDA(cudaFuncSetAttribute(k1_scan<MODE_SLOTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem) + 1024));
+        XM_CHECK_CUDA(cudaFuncSetAttribute(k1_scan<MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem) + 1024));
         XM_CHECK_CUDA(cudaFuncSetAttribute(k1_readout_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2Smem) + 1024));
         attr_done = true;
     }
@@ -596,6 +701,7 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
 
     uint8_t* ws = (uint8_t*)a->workspace;
     float* cand = (float*)ws;            ws += align_up((size_t)K1_MAX_SPLIT * hw_pad * LISTK * 4, 256);
+    float* tau_lo = (float*)ws;          ws += align_up((size_t)hw_pad * 4, 256);
     float* tau = (float*)ws;             ws += align_up((size_t)hw_pad * 4, 256);
     float* inv_den = (float*)ws;         ws += align_up((size_t)hw_pad * 4, 256);
     float* partial = (float*)ws;
@@ -625,30 +731,36 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
         for (int s = sg.nseg; s < 4; ++s) sg.tile0[s] = tiles;
         XM_REQUIRE(cols >= a->top_k, "xm_affinity_readout: group %d sees %d memory columns < top_k=%d (torch.topk would raise)", g, cols, a->top_k);
 
-        // pass 1
-        int nsplit1 = (sms + qtiles - 1) / qtiles;
-        nsplit1 = nsplit1 < 1 ? 1 : nsplit1;
-        if (nsplit1 > K1_MAX_SPLIT) nsplit1 = K1_MAX_SPLIT;
+        // scan A (slot maxima) -> tau_lo ; scan B (collect > pred(tau_lo)) -> tau, 1/den
+        int nsplit1 = sms / qtiles;                       // one wave: qtiles * nsplit <= #SMs
+        if (nsplit1 < 1) nsplit1 = 1;
+        if (nsplit1 > K1_MAX_SPLIT / 2) nsplit1 = K1_MAX_SPLIT / 2;
         if (nsplit1 > tiles) nsplit1 = tiles;
         int tps1 = (tiles + nsplit1 - 1) / nsplit1;
         nsplit1 = (tiles + tps1 - 1) / tps1;
-        k1_topk_pass1<<<dim3(qtiles, nsplit1), 192, sizeof(P1Smem) + 1024, stream>>>(
-            maps, sg, a->bsq, hw, hw_pad, a->top_k, tps1, cand, g == 0 ? a->debug_scores : nullptr);
+        k1_scan<MODE_SLOTMAX><<<dim3(qtiles, nsplit1), SCAN_THREADS, sizeof(ScanSmem) + 1024, stream>>>(
+            maps, sg, a->bsq, nullptr, hw_pad, tps1, cand, g == 0 ? a->debug_scores : nullptr);
         XM_CHECK_CUDA(cudaGetLastError());
-        k1_topk_merge<<<(hw_pad + 3) / 4, 128, 0, stream>>>(cand, nsplit1, hw, hw_pad, a->top_k, tau, inv_den);
+        k1_topk_merge<<<(hw_pad + 3) / 4, 128, 0, stream>>>(cand, nsplit1 * 2, hw, hw_pad, a->top_k, 0, tau_lo, nullptr);
+        XM_CHECK_CUDA(cudaGetLastError());
+        k1_scan<MODE_COLLECT><<<dim3(qtiles, nsplit1), SCAN_THREADS, sizeof(ScanSmem) + 1024, stream>>>(
+            maps, sg, a->bsq, tau_lo, hw_pad, tps1, cand, nullptr);
+        XM_CHECK_CUDA(cudaGetLastError());
+        k1_topk_merge<<<(hw_pad + 3) / 4, 128, 0, stream>>>(cand, nsplit1 * 2, hw, hw_pad, a->top_k, 1, tau, inv_den);
         XM_CHECK_CUDA(cudaGetLastError());
 
         // pass 2
         const int ctas_per_slice = qtiles * 2 * gr.n_obj;
-        int nsplit2 = (sms + ctas_per_slice - 1) / ctas_per_slice;
+        int nsplit2 = sms / ctas_per_slice;               // one wave
         nsplit2 = nsplit2 < 1 ? 1 : nsplit2;
         if (nsplit2 > K1_MAX_SPLIT) nsplit2 = K1_MAX_SPLIT;
         if (nsplit2 > tiles) nsplit2 = tiles;
         int tps2 = (tiles + nsplit2 - 1) / nsplit2;
         nsplit2 = (tiles + tps2 - 1) / tps2;
-        k1_readout_pass2<<<dim3(qtiles, 2 * gr.n_obj, nsplit2), 192, sizeof(P2Smem) + 1024, stream>>>(
+        k1_readout_pass2<<<dim3(qtiles, 2 * gr.n_obj, nsplit2), SCAN_THREADS, sizeof(P2Smem) + 1024, stream>>>(
             maps, sg, a->bsq, tau, inv_den, hw_pad, gr.obj_begin, gr.n_obj, tps2, g == 0 ? 1 : 0, partial);
         XM_CHECK_CUDA(cudaGetLastError());
+        xm_count_launches(6);
         k1_finish<<<dim3((hw + 31) / 32, XM_CV / 32, gr.n_obj), dim3(32, 8), 0, stream>>>(
             partial, nsplit2, gr.n_obj, hw, hw_pad, gr.obj_begin, (__half*)a->readout_chw, (__half*)a->readout_hwc);
         XM_CHECK_CUDA(cudaGetLastError());

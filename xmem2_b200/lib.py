@@ -45,7 +45,18 @@ class XmConvArgs(C.Structure):
                 ('ksize', C.c_int32), ('stride', C.c_int32), ('weight', C.c_void_p), ('bias', C.c_void_p),
                 ('cout', C.c_int32), ('cout_pad', C.c_int32), ('residual', C.c_void_p), ('residual_broadcast', C.c_int32),
                 ('relu', C.c_int32), ('out', C.c_void_p), ('out_relu', C.c_void_p), ('out_stride', C.c_int32),
-                ('out_offset', C.c_int32)]
+                ('out_offset', C.c_int32), ('workspace', C.c_void_p), ('workspace_bytes', C.c_int64)]
+
+
+_conv_ws = {}
+
+
+def conv_workspace(device):
+    """per-device split-K scratch (zeroed counters + partial tiles); allocated once."""
+    key = str(device)
+    if key not in _conv_ws:
+        _conv_ws[key] = torch.zeros(65536 * 4 + 48 * 1024 * 1024, dtype=torch.uint8, device=device)
+    return _conv_ws[key]
 
 
 _lib = None
@@ -69,6 +80,7 @@ def load() -> C.CDLL:
         lib.xm_conv2d_nhwc.argtypes = [C.POINTER(XmConvArgs), C.c_void_p]
         vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
         lib.xm_debug_last_trap.argtypes = [C.POINTER(C.c_int)]
+        lib.xm_launch_count.restype = C.c_longlong
         lib.xm_im2col_stem.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
         lib.xm_maxpool3x3s2.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
         lib.xm_relu.argtypes = [vp, vp, i64, vp]
@@ -158,5 +170,7 @@ def conv2d_nhwc(srcs, weight, bias, cout, ksize=3, stride=1, relu=False, residua
     ref = out if out is not None else out_relu
     a.out, a.out_relu = ptr(out), ptr(out_relu)
     a.out_stride, a.out_offset = ref.shape[3], out_offset
+    ws = conv_workspace(t0.device)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     check(load().xm_conv2d_nhwc(C.byref(a), stream_ptr()), 'xm_conv2d_nhwc')
     return out, out_relu

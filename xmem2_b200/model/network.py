@@ -199,7 +199,7 @@ class XMem(nn.Module):
         g1 = self._conv(prefix + '.block1.conv2', [(t1, False)], residual=ds)
         w1, b1, w2, b2, w7, b7 = self._pk[prefix + '.cbam']
         B, H, W, Cc = g1.shape
-        scratch = torch.empty(3 * B * Cc + 2 * B * H * W, dtype=torch.float32, device=g1.device)
+        scratch = torch.empty(33 * B * Cc + 2 * B * H * W, dtype=torch.float32, device=g1.device)
         gs = torch.empty_like(g1); gsr = torch.empty_like(g1)
         lib.check(lib.load().xm_cbam(g1.data_ptr(), B, H, W, Cc, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
                                      w7.data_ptr(), C.c_float(b7), scratch.data_ptr(), gs.data_ptr(), gsr.data_ptr(),
