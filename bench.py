@@ -69,37 +69,40 @@ def run_clip(core_factory, frames, masks, device, host_io, sync_each=False):
 
 
 class ClockSampler:
+    """SM clock + throttle reasons sampled in-process through NVML every 100 ms during the timed region."""
+
     def __init__(self, index):
         self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+        self.max_mhz = None
 
     def _loop(self):
-        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
-        while not self._stop.is_set():
-            try:
-                o = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
-                                   capture_output=True, text=True, timeout=5).stdout.strip().split(',')
-                self.samples.append([x.strip() for x in o])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self._stop.is_set():
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons') \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((mhz, r))
+                self._stop.wait(0.1)
+        except Exception as e:          # never let the sampler break the benchmark
+            self.error = str(e)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._loop, daemon=True); self._t.start(); return self
 
     def __exit__(self, *a):
-        self._stop.set(); self._t.join(timeout=6)
+        self._stop.set(); self._t.join(timeout=3)
 
     def summary(self):
-        sm = sorted(int(s[0]) for s in self.samples if len(s) >= 6 and s[0].isdigit())
-        if not sm:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
-        reasons = set()
-        for s in self.samples:
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[2:6]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': int(self.samples[0][1]), 'reasons': sorted(reasons)}
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': [], 'note': getattr(self, 'error', 'no samples')}
+        sm = sorted(s[0] for s in self.samples)
+        bits = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
+        reasons = sorted({name for _, r in self.samples for bit, name in bits.items() if r & bit})
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': self.max_mhz, 'reasons': reasons, 'samples': len(sm)}
 
 
 def k1_roofline(device):

@@ -73,10 +73,17 @@ typedef struct {
     void* workspace;        /* >= xm_affinity_workspace_bytes()                                         */
     int64_t workspace_bytes;
     float* debug_scores;    /* optional fp32 [N_group0][hw_pad] dump of the similarity (tests only)     */
+    int32_t plan_is_resident; /* 1: the first 4096 workspace bytes already hold the plan written by xm_affinity_plan
+                                 (CUDA-graph replay: bank sizes change without re-recording the launches);
+                                 0: build and upload it inside the call                                    */
 } xm_affinity_args_t;
 
 int64_t xm_affinity_workspace_bytes(int32_t hw, int32_t n_obj_total);
 int xm_affinity_readout(const xm_affinity_args_t* args, void* stream);
+/* host only: validate banks/groups and write the 4096-byte column-range plan the kernels read from the head of
+ * the workspace (copy it there with any stream-ordered H2D copy).  Launch shapes of xm_affinity_readout depend only
+ * on (hw, n_obj_total, group object counts), never on bank sizes.                                          */
+int xm_affinity_plan(const xm_affinity_args_t* args, void* host_plan_out, int64_t bytes);
 
 /* key [hw][64] fp16 (NHWC), selection [hw][64] fp16 -> qp [hw_pad][128] = (-e, 2*k*e), bsq = sum_c e*k^2 */
 int xm_query_pack(const void* key_hwc, const void* sel_hwc, int32_t hw, int32_t hw_pad, void* qp, float* bsq, void* stream);

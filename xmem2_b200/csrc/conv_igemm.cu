@@ -61,6 +61,7 @@ struct ConvSmem {
     uint64_t done;
     uint32_t tmem_base;
     int is_last;
+    float bias[BN];
 };
 
 template <int BN, int CONV_STAGES>
@@ -99,6 +100,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
 
     if (warp == 0) {
         if (lane == 0) {
+            tma_prefetch_desc(&maps.w);
+            for (int s = 0; s < p.n_src; ++s) tma_prefetch_desc(&maps.a[s]);
             for (int it = 0; it < ksteps; ++it) {
                 const int kk = k_begin + it;
                 const int tap = kk / cb_total;
@@ -147,6 +150,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
         const bool pix_ok = (yo < p.Ho) && (xo < p.Wo);
         const size_t pix = ((size_t)b * p.Ho + yo) * p.Wo + xo;
         const size_t rpix = ((size_t)(p.residual_bcast ? 0 : b) * p.Ho + yo) * p.Wo + xo;
+        // overlap with the main loop: stage this CTA's bias slice in shared memory
+        for (int t = row; t < BN; t += 128) sm.bias[t] = (n0 + t < p.cout) ? __ldg(p.bias + n0 + t) : 0.f;
+        asm volatile("bar.sync 2, 128;" ::: "memory");
         mbar_wait(&sm.done, 0, 23);
         tc_fence_after();
         const int tile_lin = blockIdx.x * gridDim.y + blockIdx.y;
@@ -199,7 +205,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
             const bool full = (n + 32 <= p.cout) && vec_ok;
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = acc[j] + ((n + j < p.cout) ? __ldg(p.bias + n + j) : 0.f);
+            for (int j = 0; j < 32; ++j) v[j] = acc[j] + sm.bias[c0 + j];
             if (p.residual) {
                 const __half* rp = p.residual + rpix * p.residual_stride + n;
                 if (full) {
@@ -360,7 +366,15 @@ extern "C" int xm_conv2d_nhwc(const xm_conv_args_t* a, void* stream_) {
     p.splits = (ksteps + p.ksteps_per_split - 1) / p.ksteps_per_split;
     p.ws_counter = (int*)a->workspace;
     p.ws_partial = a->workspace ? (float*)((char*)a->workspace + 65536 * 4) : nullptr;
-    const bool deep = ctas < 2 * sms;
-    if (BN == 128) return deep ? launch_conv<128, 6>(maps, p, a->cout_pad, stream) : launch_conv<128, 3>(maps, p, a->cout_pad, stream);
-    return deep ? launch_conv<64, 6>(maps, p, a->cout_pad, stream) : launch_conv<64, 3>(maps, p, a->cout_pad, stream);
+    // pipeline depth: short K loops want several co-resident CTAs per SM (2 stages -> 3 CTAs/SM); long K loops on
+    // small grids want a deep ring to cover the L2 latency (6 stages, 1 CTA/SM); big grids take 3 stages (2 CTAs/SM).
+    const int depth = (p.ksteps_per_split <= 4) ? 2 : ((ctas * p.splits < 2 * sms) ? 6 : 3);
+    if (BN == 128) {
+        if (depth == 2) return launch_conv<128, 2>(maps, p, a->cout_pad, stream);
+        if (depth == 3) return launch_conv<128, 3>(maps, p, a->cout_pad, stream);
+        return launch_conv<128, 6>(maps, p, a->cout_pad, stream);
+    }
+    if (depth == 2) return launch_conv<64, 2>(maps, p, a->cout_pad, stream);
+    if (depth == 3) return launch_conv<64, 3>(maps, p, a->cout_pad, stream);
+    return launch_conv<64, 6>(maps, p, a->cout_pad, stream);
 }

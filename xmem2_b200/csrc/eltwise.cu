@@ -22,28 +22,42 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 // channels: 0..2 image (shared by all b), 3 = mask[b], 4 = sum_{j!=b} mask[j]  (only when masks != null)
 __global__ void im2col_stem_kernel(const float* __restrict__ image, const float* __restrict__ masks, int n, int H, int W,
                                    int C, int kpad, __half* __restrict__ out) {
-    const int Ho = H / 2, Wo = W / 2;
-    const size_t total = (size_t)n * Ho * Wo * kpad;
+    // one thread = 8 consecutive k of one output pixel -> one 16-byte store (coalesced across the warp)
+    const int Ho = H / 2, Wo = W / 2, K8 = kpad / 8;
+    const size_t total = (size_t)n * Ho * Wo * K8;
+    const size_t plane = (size_t)H * W;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int k = i % kpad;
-        size_t p = i / kpad;
+        const int k8 = i % K8;
+        size_t p = i / K8;
         const int xo = p % Wo; p /= Wo;
         const int yo = p % Ho;
         const int b = p / Ho;
-        float v = 0.f;
-        if (k < 49 * C) {
-            const int c = k % C, tap = k / C;
-            const int y = 2 * yo + tap / 7 - 3, x = 2 * xo + tap % 7 - 3;
-            if (y >= 0 && y < H && x >= 0 && x < W) {
-                const size_t off = (size_t)y * W + x;
-                if (c < 3) v = image[(size_t)c * H * W + off];
-                else if (c == 3) v = masks[(size_t)b * H * W + off];
-                else {
-                    for (int j = 0; j < n; ++j) if (j != b) v += masks[(size_t)j * H * W + off];
+        float v[8];
+        int k = k8 * 8;
+        int tap = k / C, c = k - tap * C;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float val = 0.f;
+            if (tap < 49) {
+                const int y = 2 * yo + tap / 7 - 3, x = 2 * xo + tap % 7 - 3;
+                if (y >= 0 && y < H && x >= 0 && x < W) {
+                    const size_t off = (size_t)y * W + x;
+                    if (c < 3) val = __ldg(image + c * plane + off);
+                    else if (c == 3) val = __ldg(masks + b * plane + off);
+                    else {
+                        for (int j = 0; j < n; ++j) if (j != b) val += __ldg(masks + j * plane + off);
+                    }
                 }
             }
+            v[e] = val;
+            if (++c == C) { c = 0; ++tap; }
         }
-        out[i] = __float2half_rn(v);
+        uint4 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&(const __half2&)__floats2half2_rn(v[0], v[1]));
+        u.y = *reinterpret_cast<const uint32_t*>(&(const __half2&)__floats2half2_rn(v[2], v[3]));
+        u.z = *reinterpret_cast<const uint32_t*>(&(const __half2&)__floats2half2_rn(v[4], v[5]));
+        u.w = *reinterpret_cast<const uint32_t*>(&(const __half2&)__floats2half2_rn(v[6], v[7]));
+        reinterpret_cast<uint4*>(out)[i] = u;
     }
 }
 
@@ -364,7 +378,7 @@ extern "C" int xm_im2col_stem(const float* image, const float* masks, int32_t n,
     XM_REQUIRE(image && out && n >= 1 && H % 2 == 0 && W % 2 == 0, "xm_im2col_stem: bad arguments");
     const int C = masks ? 5 : 3;
     XM_REQUIRE(kpad >= 49 * C && kpad % 64 == 0, "xm_im2col_stem: kpad must be a multiple of 64 >= %d", 49 * C);
-    const size_t total = (size_t)n * (H / 2) * (W / 2) * kpad;
+    const size_t total = (size_t)n * (H / 2) * (W / 2) * (kpad / 8);
     im2col_stem_kernel<<<grid_for(total), 256, 0, STREAM>>>(image, masks, n, H, W, C, kpad, (__half*)out);
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());

@@ -18,6 +18,7 @@
 //     reference's dense v @ affinity).  Split over column slices; k1_finish sums the slices.
 #include <cfloat>
 #include <cmath>
+#include <cstring>
 #include "common.h"
 #include "tc5.cuh"
 
@@ -148,13 +149,17 @@ __device__ __forceinline__ float score2(uint32_t acc_bits, float bsq8, float ms)
 
 template <int MODE>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
-k1_scan(const __grid_constant__ K1Maps maps, const K1Seg sg, const float* __restrict__ bsq, const float* __restrict__ tau_lo,
-        int hw_pad, int tiles_per_split, float* __restrict__ cand, float* __restrict__ dbg_scores) {
+k1_scan(const __grid_constant__ K1Maps maps, const K1Seg* __restrict__ sgp, const float* __restrict__ bsq, const float* __restrict__ tau_lo,
+        int hw_pad, float* __restrict__ cand, float* __restrict__ dbg_scores) {
     extern __shared__ uint8_t smem_raw[];
     ScanSmem& sm = *reinterpret_cast<ScanSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ K1Seg sg;                       // column-range table lives in device memory (CUDA-graph friendly)
+    if (threadIdx.x < sizeof(K1Seg) / 4) reinterpret_cast<uint32_t*>(&sg)[threadIdx.x] = reinterpret_cast<const uint32_t*>(sgp)[threadIdx.x];
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x, split = blockIdx.y;
     const int total_tiles = sg.tile0[sg.nseg];
+    const int tiles_per_split = (total_tiles + gridDim.y - 1) / gridDim.y;
     const int t_begin = split * tiles_per_split;
     const int t_end = min(total_tiles, t_begin + tiles_per_split);
     const int nt = max(0, t_end - t_begin);
@@ -385,16 +390,20 @@ struct P2Smem {
 };
 
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
-k1_readout_pass2(const __grid_constant__ K1Maps maps, const K1Seg sg, const float* __restrict__ bsq,
+k1_readout_pass2(const __grid_constant__ K1Maps maps, const K1Seg* __restrict__ sgp, const float* __restrict__ bsq,
                  const float* __restrict__ tau, const float* __restrict__ inv_den, int hw_pad, int obj_begin,
-                 int n_obj, int tiles_per_split, int do_usage, float* __restrict__ partial) {
+                 int n_obj, int do_usage, float* __restrict__ partial) {
     extern __shared__ uint8_t smem_raw[];
     P2Smem& sm = *reinterpret_cast<P2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ K1Seg sg;
+    if (threadIdx.x < sizeof(K1Seg) / 4) reinterpret_cast<uint32_t*>(&sg)[threadIdx.x] = reinterpret_cast<const uint32_t*>(sgp)[threadIdx.x];
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x;
     const int obj = blockIdx.y >> 1, chalf = blockIdx.y & 1;       // local object index within the group
     const int split = blockIdx.z;
     const int total_tiles = sg.tile0[sg.nseg];
+    const int tiles_per_split = (total_tiles + gridDim.z - 1) / gridDim.z;
     const int t_begin = split * tiles_per_split;
     const int t_end = min(total_tiles, t_begin + tiles_per_split);
     const int nt = max(0, t_end - t_begin);
@@ -642,14 +651,56 @@ extern "C" int xm_key_pack(const void* key_hwc, int32_t n, void* dst_rows, void*
 }
 
 static const int K1_MAX_SPLIT = 32;
+static const int K1_PLAN_BYTES = 4096;          // XM_MAX_GROUPS segment tables at the head of the workspace
 
 extern "C" int64_t xm_affinity_workspace_bytes(int32_t hw, int32_t n_obj_total) {
     const int64_t hw_pad = (hw + TQ - 1) / TQ * TQ;
-    int64_t b = 0;
+    int64_t b = K1_PLAN_BYTES;
     b += align_up((size_t)K1_MAX_SPLIT * hw_pad * LISTK * 4, 256);        // candidates
     b += 3 * align_up((size_t)hw_pad * 4, 256);                           // tau_lo, tau, inv_den
     b += align_up((size_t)K1_MAX_SPLIT * n_obj_total * XM_CV * hw_pad * 4, 256);   // partial readouts
     return b;
+}
+
+static_assert(sizeof(K1Seg) * XM_MAX_GROUPS <= K1_PLAN_BYTES, "plan area too small");
+static_assert(sizeof(K1Seg) % 4 == 0 && sizeof(K1Seg) / 4 <= SCAN_THREADS, "K1Seg is copied by one thread per word");
+
+// Build the per-group column-range tables (host side).  plan_out receives XM_MAX_GROUPS K1Seg records.
+static int k1_build_plan(const xm_affinity_args_t* a, K1Seg* plan) {
+    XM_REQUIRE(a->n_groups > 0 && a->n_groups <= XM_MAX_GROUPS, "xm_affinity: bad n_groups %d", a->n_groups);
+    for (int g = 0; g < a->n_groups; ++g) {
+        const xm_group_t& gr = a->groups[g];
+        XM_REQUIRE(gr.n_obj > 0 && gr.obj_begin >= 0 && gr.obj_begin + gr.n_obj <= a->n_obj_total, "xm_affinity: bad group %d objects", g);
+        K1Seg& sg = plan[g];
+        sg.nseg = 0;
+        int tiles = 0, cols = 0;
+        for (int i = 0; i < 3; ++i) {
+            const xm_bank_t& bk = a->banks[i];
+            sg.shr[i] = nullptr; sg.usage[i] = nullptr; sg.bank[i] = 0; sg.begin[i] = 0; sg.end[i] = 0; sg.col0[i] = 0; sg.origin[i] = 0;
+            if (bk.size <= 0 || !bk.keys) continue;
+            XM_REQUIRE(bk.cap % 8 == 0 && bk.size <= bk.cap, "xm_affinity: bank %d cap must be a multiple of 8 and >= size", i);
+            XM_REQUIRE(bk.shrinkage && bk.values && bk.n_obj_cap > 0, "xm_affinity: bank %d has null shrinkage/values", i);
+            const int begin = gr.begin[i];
+            XM_REQUIRE(begin >= 0 && begin <= bk.size, "xm_affinity: group %d bank %d begin %d outside [0,%d]", g, i, begin, bk.size);
+            if (begin == bk.size) continue;
+            XM_REQUIRE(gr.obj_begin + gr.n_obj <= bk.n_obj_cap, "xm_affinity: bank %d holds fewer value planes than group %d needs", i, g);
+            const int s = sg.nseg++;
+            sg.bank[s] = i; sg.begin[s] = begin; sg.end[s] = bk.size; sg.tile0[s] = tiles; sg.col0[s] = cols;
+            sg.origin[s] = begin & ~7;
+            sg.shr[s] = bk.shrinkage; sg.usage[s] = (g == 0) ? bk.usage : nullptr;
+            tiles += (bk.size - sg.origin[s] + TN - 1) / TN;
+            cols += bk.size - begin;
+        }
+        for (int s = sg.nseg; s < 4; ++s) sg.tile0[s] = tiles;
+        XM_REQUIRE(cols >= a->top_k, "xm_affinity: group %d sees %d memory columns < top_k=%d (torch.topk would raise)", g, cols, a->top_k);
+    }
+    return XM_OK;
+}
+
+extern "C" int xm_affinity_plan(const xm_affinity_args_t* a, void* host_plan_out, int64_t bytes) {
+    XM_REQUIRE(a && host_plan_out && bytes >= K1_PLAN_BYTES, "xm_affinity_plan: need a %d-byte host buffer", K1_PLAN_BYTES);
+    memset(host_plan_out, 0, K1_PLAN_BYTES);
+    return k1_build_plan(a, (K1Seg*)host_plan_out);
 }
 
 extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
@@ -673,6 +724,23 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
         attr_done = true;
     }
 
+    uint8_t* ws = (uint8_t*)a->workspace;
+    K1Seg* plan_dev = (K1Seg*)ws;        ws += K1_PLAN_BYTES;
+    float* cand = (float*)ws;            ws += align_up((size_t)K1_MAX_SPLIT * hw_pad * LISTK * 4, 256);
+    float* tau_lo = (float*)ws;          ws += align_up((size_t)hw_pad * 4, 256);
+    float* tau = (float*)ws;             ws += align_up((size_t)hw_pad * 4, 256);
+    float* inv_den = (float*)ws;         ws += align_up((size_t)hw_pad * 4, 256);
+    float* partial = (float*)ws;
+
+    if (!a->plan_is_resident) {
+        // eager convenience path: build the table here and copy it (pageable source: staged before the call returns)
+        K1Seg plan[XM_MAX_GROUPS];
+        memset(plan, 0, sizeof(plan));
+        const int rc = k1_build_plan(a, plan);
+        if (rc != XM_OK) return rc;
+        XM_CHECK_CUDA(cudaMemcpyAsync(plan_dev, plan, sizeof(K1Seg) * a->n_groups, cudaMemcpyHostToDevice, stream));
+    }
+
     K1Maps maps;
     {
         uint64_t d[2] = {KP, (uint64_t)hw_pad};
@@ -687,8 +755,6 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
             maps.v[i] = maps.q;
             continue;
         }
-        XM_REQUIRE(bk.cap % 8 == 0 && bk.size <= bk.cap, "xm_affinity_readout: bank %d cap must be a multiple of 8 and >= size", i);
-        XM_REQUIRE(bk.shrinkage && bk.values && bk.n_obj_cap > 0, "xm_affinity_readout: bank %d has null shrinkage/values", i);
         uint64_t d[2] = {KP, (uint64_t)bk.cap};
         uint64_t s[1] = {KP * 2};
         uint32_t b[2] = {64, TN};
@@ -699,52 +765,23 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
         if (xm_make_tmap_f16(&maps.v[i], bk.values, 3, dv, sv, bv)) return XM_ERR_CUDA;
     }
 
-    uint8_t* ws = (uint8_t*)a->workspace;
-    float* cand = (float*)ws;            ws += align_up((size_t)K1_MAX_SPLIT * hw_pad * LISTK * 4, 256);
-    float* tau_lo = (float*)ws;          ws += align_up((size_t)hw_pad * 4, 256);
-    float* tau = (float*)ws;             ws += align_up((size_t)hw_pad * 4, 256);
-    float* inv_den = (float*)ws;         ws += align_up((size_t)hw_pad * 4, 256);
-    float* partial = (float*)ws;
-
+    // launch shapes depend only on (hw, n_obj): one wave of CTAs, each owning a contiguous slice of column tiles
     const int sms = xm_num_sms();
+    int nsplit1 = sms / qtiles;
+    if (nsplit1 < 1) nsplit1 = 1;
+    if (nsplit1 > K1_MAX_SPLIT / 2) nsplit1 = K1_MAX_SPLIT / 2;
     for (int g = 0; g < a->n_groups; ++g) {
         const xm_group_t& gr = a->groups[g];
         XM_REQUIRE(gr.n_obj > 0 && gr.obj_begin >= 0 && gr.obj_begin + gr.n_obj <= a->n_obj_total, "xm_affinity_readout: bad group %d objects", g);
-        K1Seg sg;
-        sg.nseg = 0;
-        int tiles = 0, cols = 0;
-        for (int i = 0; i < 3; ++i) {
-            const xm_bank_t& bk = a->banks[i];
-            sg.shr[i] = nullptr; sg.usage[i] = nullptr; sg.bank[i] = 0; sg.begin[i] = 0; sg.end[i] = 0; sg.col0[i] = 0; sg.origin[i] = 0;
-            if (bk.size <= 0 || !bk.keys) continue;
-            const int begin = gr.begin[i];
-            XM_REQUIRE(begin >= 0 && begin <= bk.size, "xm_affinity_readout: group %d bank %d begin %d outside [0,%d]", g, i, begin, bk.size);
-            if (begin == bk.size) continue;
-            XM_REQUIRE(gr.obj_begin + gr.n_obj <= bk.n_obj_cap, "xm_affinity_readout: bank %d holds fewer value planes than group %d needs", i, g);
-            const int s = sg.nseg++;
-            sg.bank[s] = i; sg.begin[s] = begin; sg.end[s] = bk.size; sg.tile0[s] = tiles; sg.col0[s] = cols;
-            sg.origin[s] = begin & ~7;
-            sg.shr[s] = bk.shrinkage; sg.usage[s] = (g == 0) ? bk.usage : nullptr;
-            tiles += (bk.size - sg.origin[s] + TN - 1) / TN;
-            cols += bk.size - begin;
-        }
-        for (int s = sg.nseg; s < 4; ++s) sg.tile0[s] = tiles;
-        XM_REQUIRE(cols >= a->top_k, "xm_affinity_readout: group %d sees %d memory columns < top_k=%d (torch.topk would raise)", g, cols, a->top_k);
-
+        const K1Seg* sgp = plan_dev + g;
         // scan A (slot maxima) -> tau_lo ; scan B (collect > pred(tau_lo)) -> tau, 1/den
-        int nsplit1 = sms / qtiles;                       // one wave: qtiles * nsplit <= #SMs
-        if (nsplit1 < 1) nsplit1 = 1;
-        if (nsplit1 > K1_MAX_SPLIT / 2) nsplit1 = K1_MAX_SPLIT / 2;
-        if (nsplit1 > tiles) nsplit1 = tiles;
-        int tps1 = (tiles + nsplit1 - 1) / nsplit1;
-        nsplit1 = (tiles + tps1 - 1) / tps1;
         k1_scan<MODE_SLOTMAX><<<dim3(qtiles, nsplit1), SCAN_THREADS, sizeof(ScanSmem) + 1024, stream>>>(
-            maps, sg, a->bsq, nullptr, hw_pad, tps1, cand, g == 0 ? a->debug_scores : nullptr);
+            maps, sgp, a->bsq, nullptr, hw_pad, cand, g == 0 ? a->debug_scores : nullptr);
         XM_CHECK_CUDA(cudaGetLastError());
         k1_topk_merge<<<(hw_pad + 3) / 4, 128, 0, stream>>>(cand, nsplit1 * 2, hw, hw_pad, a->top_k, 0, tau_lo, nullptr);
         XM_CHECK_CUDA(cudaGetLastError());
         k1_scan<MODE_COLLECT><<<dim3(qtiles, nsplit1), SCAN_THREADS, sizeof(ScanSmem) + 1024, stream>>>(
-            maps, sg, a->bsq, tau_lo, hw_pad, tps1, cand, nullptr);
+            maps, sgp, a->bsq, tau_lo, hw_pad, cand, nullptr);
         XM_CHECK_CUDA(cudaGetLastError());
         k1_topk_merge<<<(hw_pad + 3) / 4, 128, 0, stream>>>(cand, nsplit1 * 2, hw, hw_pad, a->top_k, 1, tau, inv_den);
         XM_CHECK_CUDA(cudaGetLastError());
@@ -754,11 +791,8 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
         int nsplit2 = sms / ctas_per_slice;               // one wave
         nsplit2 = nsplit2 < 1 ? 1 : nsplit2;
         if (nsplit2 > K1_MAX_SPLIT) nsplit2 = K1_MAX_SPLIT;
-        if (nsplit2 > tiles) nsplit2 = tiles;
-        int tps2 = (tiles + nsplit2 - 1) / nsplit2;
-        nsplit2 = (tiles + tps2 - 1) / tps2;
         k1_readout_pass2<<<dim3(qtiles, 2 * gr.n_obj, nsplit2), SCAN_THREADS, sizeof(P2Smem) + 1024, stream>>>(
-            maps, sg, a->bsq, tau, inv_den, hw_pad, gr.obj_begin, gr.n_obj, tps2, g == 0 ? 1 : 0, partial);
+            maps, sgp, a->bsq, tau, inv_den, hw_pad, gr.obj_begin, gr.n_obj, g == 0 ? 1 : 0, partial);
         XM_CHECK_CUDA(cudaGetLastError());
         xm_count_launches(6);
         k1_finish<<<dim3((hw + 31) / 32, XM_CV / 32, gr.n_obj), dim3(32, 8), 0, stream>>>(

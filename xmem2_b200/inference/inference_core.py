@@ -8,6 +8,9 @@ The frame scheduling rules are those of `InferenceCore.step` (:62-152); all heav
 """
 from __future__ import annotations
 
+import os
+import time
+
 import torch
 
 from ..model.aggregate import aggregate
@@ -26,6 +29,12 @@ class InferenceCore:
         self.deep_update_sync = self.deep_update_every < 0     # deep update rides on memory frames
         self.clear_memory()
         self.all_labels = None
+        # steady-state frames (no mask, not a memory frame) are replayed from a CUDA graph: ~90 kernel launches per
+        # frame would otherwise be bound by host launch latency, not by the GPU.  `use_cuda_graph=False` disables it.
+        self.use_cuda_graph = config.get('use_cuda_graph', True)
+        self._graph = None
+        self._graph_sig = None
+        self._graph_warm_sig = None
         # warm-up on the network's own device (the reference hard-codes cuda:0, inference_core.py:26)
         dev = next(network.parameters()).device
         if dev.type == 'cuda':
@@ -37,6 +46,8 @@ class InferenceCore:
         if not self.deep_update_sync:
             self.last_deep_update_ti = -self.deep_update_every
         self.memory = self.memory.copy_perm_mem_only() if keep_permanent else MemoryManager(config=self.config)
+        self._graph = None
+        self._graph_sig = None
 
     def update_config(self, config):
         self.mem_every = config['mem_every']
@@ -76,6 +87,13 @@ class InferenceCore:
         image = self._prepare(image)
         is_mem_frame, is_deep_update, is_normal_update = self._schedule(mask is not None, end, manually_curated_masks)
         need_segment = (valid_labels is None) or (len(self.all_labels) != len(valid_labels))
+
+        if (self.use_cuda_graph and mask is None and need_segment and is_normal_update and not is_mem_frame and not end
+                and not disable_memory_updates and not return_key_and_stuff and image.is_cuda
+                and self.memory.get_hidden() is not None):
+            prob = self._graph_step(image)
+            if prob is not None:
+                return unpad(prob, self.pad)
 
         key, shrinkage, selection, f16, f8, f4 = self.network.encode_key(
             image, need_ek=(self.enable_long_term or need_segment), need_sk=True)
@@ -121,6 +139,55 @@ class InferenceCore:
         if return_key_and_stuff:
             return res, key, shrinkage, selection
         return res
+
+    # ------------------------------------------------------------------ CUDA-graph replay of steady-state frames
+    def _graph_step(self, image):
+        """encode_key -> match_memory -> segment(h_out=True) -> hidden update for one ordinary frame, replayed from a
+        recorded CUDA graph.  The graph depends on the image shape and on the memory arenas' addresses/capacities and
+        group structure (MemoryManager.layout_signature); bank SIZES live in a device-side plan that is refreshed
+        (stream ordered) whenever a memory frame changed them.  Returns None when this frame must run eagerly
+        (first frame with a new signature = warm-up of lazily initialised kernel state)."""
+        mem = self.memory
+        sig = (tuple(image.shape), mem.layout_signature(), len(self.all_labels))
+        if self._graph is None or self._graph_sig != sig:
+            if self._graph_warm_sig != sig:
+                self._graph_warm_sig = sig          # run this frame eagerly, record on the next one
+                self._graph = None
+                return None
+            self._capture(image, sig)
+        hid = mem.get_hidden()
+        if hid.data_ptr() != self._g_hidden.data_ptr():
+            self._g_hidden.copy_(hid)
+            mem.set_hidden(self._g_hidden)
+        self._g_image.copy_(image)
+        h, w = image.shape[-2] // 16, image.shape[-1] // 16
+        mem.upload_plan(h * w, image.device)
+        self._graph.replay()
+        return self._g_prob
+
+    def _capture(self, image, sig):
+        t0 = time.perf_counter()
+        mem, net = self.memory, self.network
+        dev = image.device
+        n = len(self.all_labels)
+        h, w = image.shape[-2] // 16, image.shape[-1] // 16
+        self._g_image = image.clone()
+        self._g_hidden = torch.zeros((1, n, h, w, mem.hidden_dim), device=dev).permute(0, 1, 4, 2, 3)
+        self._g_hidden.copy_(mem.get_hidden())
+        mem.set_hidden(self._g_hidden)
+        mem.upload_plan(h * w, dev)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            key, _, selection, f16, f8, f4 = net.encode_key(self._g_image, need_ek=True, need_sk=True)
+            readout = mem.match_memory(key, selection).unsqueeze(0)
+            hidden, _, prob = net.segment((f16, f8, f4), readout, self._g_hidden, h_out=True, strip_bg=False)
+            self._g_hidden.copy_(hidden)
+            self._g_prob = prob[0]
+        self._graph, self._graph_sig = graph, sig
+        if os.environ.get('XMEM_TRACE'):
+            torch.cuda.synchronize(dev)
+            print(f'[xmem2_b200] recorded frame graph in {time.perf_counter() - t0:.3f}s', flush=True)
 
     def put_to_permanent_memory(self, image, mask, ti=None):
         """encode an annotated frame straight into permanent memory (inference_core.py:154-179)."""

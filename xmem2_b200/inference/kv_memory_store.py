@@ -186,8 +186,9 @@ class KeyValueMemoryStore:
         self._life[:self._n] += 1
 
     def tick_life(self):
-        if self.count_usage and self._n > 0:
-            self._life[:self._n] += 1
+        # whole arena (static shape: CUDA-graph friendly); slots beyond `size` are re-initialised by add()
+        if self.count_usage and self._life is not None:
+            self._life += 1
 
     def get_usage(self):
         if not self.count_usage:

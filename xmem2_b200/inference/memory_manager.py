@@ -41,6 +41,9 @@ class MemoryManager:
                                                 reserve=self.max_long_elements + self.num_prototypes)
         self.reset_config = True
         self._ws = None
+        self._plan_key = None
+        self._plan_host = None
+        self.HW = None
 
     def update_config(self, config):
         self.reset_config = True
@@ -55,34 +58,20 @@ class MemoryManager:
             self.max_long_elements = config['max_long_term_elements']
 
     # ------------------------------------------------------------------ memory read (reference :61-190)
-    def match_memory(self, query_key, selection, disable_usage_updates=False):
-        """query_key, selection: [1, CK, h, w] -> readout [n_obj, CV, h, w] (fp16, NHWC-backed view)."""
-        lib.require_cuda(query_key, 'query_key')
-        if selection is None:
-            raise NotImplementedError('the fused read kernel needs the selection term (enable_long_term or need_segment path)')
-        h, w = query_key.shape[-2:]
-        hw = h * w
-        hw_pad = (hw + 127) // 128 * 128
-        dev = query_key.device
-        krows = query_key[0].permute(1, 2, 0).reshape(hw, -1)
-        erows = selection[0].permute(1, 2, 0).reshape(hw, -1)
-        krows = krows.to(torch.float16).contiguous(); erows = erows.to(torch.float16).contiguous()
-        qp, bsq = lib.query_pack(krows, erows, hw_pad)
-
+    def _read_args(self, n_obj_hint=None):
+        """XmAffinityArgs describing the three banks and the object groups (no query yet)."""
         temp, perm = self.temporary_work_mem, self.permanent_work_mem
-        use_long = self.enable_long_term and self.long_mem.engaged()
+        use_long = self.enable_long_term and self.long_mem.engaged() and self.long_mem.size > 0
         num_groups = max(temp.num_groups, perm.num_groups)
-        n_obj = len(perm.all_objects) if perm.num_groups >= temp.num_groups else len(temp.all_objects)
         if num_groups == 0:
             raise RuntimeError('match_memory called with an empty memory')
-
+        n_obj = len(perm.all_objects) if perm.num_groups >= temp.num_groups else len(temp.all_objects)
         a = lib.XmAffinityArgs()
-        record = self.enable_long_term and not disable_usage_updates
         if use_long:
-            self.long_mem.bank_struct(a.banks[0], with_usage=record and self.enable_long_term_usage)
+            self.long_mem.bank_struct(a.banks[0], with_usage=self.enable_long_term_usage)
         else:
             a.banks[0].size = 0
-        temp.bank_struct(a.banks[1], with_usage=record)
+        temp.bank_struct(a.banks[1], with_usage=self.enable_long_term)
         perm.bank_struct(a.banks[2], with_usage=False)
         a.n_groups = num_groups
         for gi in range(num_groups):
@@ -94,17 +83,82 @@ class MemoryManager:
             g.begin[0] = self.long_mem.group_begin(gi) if (use_long and gi < self.long_mem.num_groups) else (self.long_mem.size if use_long else 0)
             g.begin[1] = temp.group_begin(gi) if gi < temp.num_groups else temp.size
             g.begin[2] = perm.group_begin(gi) if gi < perm.num_groups else perm.size
-        out = torch.empty((n_obj, hw, lib.CV), dtype=torch.float16, device=dev)
+        a.top_k, a.n_obj_total = self.top_k, n_obj
+        return a, n_obj, use_long
+
+    def layout_signature(self):
+        """Everything a recorded CUDA graph of the read depends on: arena addresses/capacities and group structure
+        (NOT the bank sizes — those live in the device-side plan)."""
+        a, n_obj, use_long = self._read_args()
+        banks = tuple((a.banks[i].keys, a.banks[i].values, a.banks[i].cap, a.banks[i].n_obj_cap, bool(a.banks[i].usage))
+                      for i in range(3))
+        groups = tuple((a.groups[g].obj_begin, a.groups[g].n_obj) for g in range(a.n_groups))
+        return banks, groups, n_obj, self.top_k
+
+    def refresh_plan(self, device, disable_usage_updates=False):
+        """(Re)compute the column-range plan when any bank size / group range / usage routing changed and copy it to
+        the head of the workspace (stream ordered).  Returns the args struct for the kernel call."""
+        a, n_obj, use_long = self._read_args()
+        if disable_usage_updates or not self.enable_long_term:
+            for i in range(3):
+                a.banks[i].usage = None
+        key = (tuple((a.banks[i].keys, a.banks[i].shrinkage, a.banks[i].values, a.banks[i].usage, a.banks[i].cap, a.banks[i].size)
+                     for i in range(3)),
+               tuple((a.groups[g].obj_begin, a.groups[g].n_obj, tuple(a.groups[g].begin)) for g in range(a.n_groups)), self.top_k)
+        if self.HW is not None:
+            wsb = lib.load().xm_affinity_workspace_bytes(self.HW, n_obj)
+        else:
+            wsb = 0
+        return a, n_obj, use_long, key
+
+    def _ensure_ws(self, hw, n_obj, device):
         wsb = lib.load().xm_affinity_workspace_bytes(hw, n_obj)
-        if self._ws is None or self._ws.numel() < wsb or self._ws.device != dev:
-            self._ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        a.qp, a.bsq, a.hw, a.hw_pad, a.top_k, a.n_obj_total = qp.data_ptr(), bsq.data_ptr(), hw, hw_pad, self.top_k, n_obj
+        if self._ws is None or self._ws.numel() < wsb or self._ws.device != device:
+            self._ws = torch.empty(wsb, dtype=torch.uint8, device=device)
+            self._plan_key = None
+        return wsb
+
+    def upload_plan(self, hw, device, disable_usage_updates=False):
+        a, n_obj, use_long, key = self.refresh_plan(device, disable_usage_updates)
+        wsb = self._ensure_ws(hw, n_obj, device)
+        if key != self._plan_key:
+            host = torch.empty(4096, dtype=torch.uint8).pin_memory()
+            lib.check(lib.load().xm_affinity_plan(C.byref(a), host.data_ptr(), 4096), 'xm_affinity_plan')
+            self._ws[:4096].copy_(host, non_blocking=True)
+            self._plan_host = host                     # keep alive until the copy has certainly run (next change)
+            self._plan_key = key
+        return a, n_obj, use_long, wsb
+
+    def match_memory(self, query_key, selection, disable_usage_updates=False):
+        """query_key, selection: [1, CK, h, w] -> readout [n_obj, CV, h, w] (fp16, NHWC-backed view)."""
+        lib.require_cuda(query_key, 'query_key')
+        if selection is None:
+            raise NotImplementedError('the fused read kernel needs the selection term (enable_long_term or need_segment path)')
+        h, w = query_key.shape[-2:]
+        hw = h * w
+        hw_pad = (hw + 127) // 128 * 128
+        dev = query_key.device
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing:
+            # plan already uploaded by the caller (InferenceCore graph path); only describe the banks
+            a, n_obj, use_long, _ = self.refresh_plan(dev, disable_usage_updates)
+            wsb = lib.load().xm_affinity_workspace_bytes(hw, n_obj)
+            assert self._ws is not None and self._ws.numel() >= wsb
+        else:
+            a, n_obj, use_long, wsb = self.upload_plan(hw, dev, disable_usage_updates)
+        krows = query_key[0].permute(1, 2, 0).reshape(hw, -1)
+        erows = selection[0].permute(1, 2, 0).reshape(hw, -1)
+        krows = krows.to(torch.float16).contiguous(); erows = erows.to(torch.float16).contiguous()
+        qp, bsq = lib.query_pack(krows, erows, hw_pad)
+        out = torch.empty((n_obj, hw, lib.CV), dtype=torch.float16, device=dev)
+        a.qp, a.bsq, a.hw, a.hw_pad = qp.data_ptr(), bsq.data_ptr(), hw, hw_pad
         a.readout_chw, a.readout_hwc = None, out.data_ptr()
         a.workspace, a.workspace_bytes = self._ws.data_ptr(), wsb
+        a.plan_is_resident = 1
         lib.check(lib.load().xm_affinity_readout(C.byref(a), lib.stream_ptr()), 'xm_affinity_readout')
-        if record:
+        if self.enable_long_term and not disable_usage_updates:
             # use_count was accumulated by the kernel; life_count += 1 (kv_memory_store.py:103)
-            temp.tick_life()
+            self.temporary_work_mem.tick_life()
             if use_long and self.enable_long_term_usage:
                 self.long_mem.tick_life()
         return out.view(n_obj, h, w, lib.CV).permute(0, 3, 1, 2)

@@ -33,7 +33,7 @@ class XmAffinityArgs(C.Structure):
                 ('qp', C.c_void_p), ('bsq', C.c_void_p), ('hw', C.c_int32), ('hw_pad', C.c_int32),
                 ('top_k', C.c_int32), ('n_obj_total', C.c_int32), ('readout_chw', C.c_void_p),
                 ('readout_hwc', C.c_void_p), ('workspace', C.c_void_p), ('workspace_bytes', C.c_int64),
-                ('debug_scores', C.c_void_p)]
+                ('debug_scores', C.c_void_p), ('plan_is_resident', C.c_int32)]
 
 
 class XmConvSrc(C.Structure):
@@ -75,6 +75,7 @@ def load() -> C.CDLL:
         lib.xm_affinity_workspace_bytes.restype = C.c_int64
         lib.xm_affinity_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
         lib.xm_affinity_readout.argtypes = [C.POINTER(XmAffinityArgs), C.c_void_p]
+        lib.xm_affinity_plan.argtypes = [C.POINTER(XmAffinityArgs), C.c_void_p, C.c_int64]
         lib.xm_query_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.xm_key_pack.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.xm_conv2d_nhwc.argtypes = [C.POINTER(XmConvArgs), C.c_void_p]
