@@ -38,6 +38,8 @@ int xm_version(void);
 int xm_debug_last_trap(int* out7);
 /* number of kernels this library has launched so far (accounting for bench.py) */
 long long xm_launch_count(void);
+/* programmatic dependent launch between this library's kernels (default on) */
+void xm_set_pdl(int on);
 
 /* ---------------------------------------------------------------- memory read (K1) */
 /* One memory bank (KeyValueMemoryStore, inference/kv_memory_store.py:4-239) as the kernel sees it. */

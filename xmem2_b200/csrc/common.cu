@@ -99,3 +99,12 @@ extern "C" int xm_debug_last_trap(int* out) {
 static std::atomic<long long> g_launches{0};
 void xm_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 extern "C" long long xm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// ---- programmatic dependent launch toggle (default on; XMEM_NO_PDL=1 or xm_set_pdl(0) turns it off) ----
+#include <cstdlib>
+static int g_pdl = -1;
+int xm_pdl_enabled() {
+    if (g_pdl < 0) { const char* e = getenv("XMEM_NO_PDL"); g_pdl = (e && e[0] == '1') ? 0 : 1; }
+    return g_pdl;
+}
+extern "C" void xm_set_pdl(int on) { g_pdl = on ? 1 : 0; }

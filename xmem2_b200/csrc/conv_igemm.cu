@@ -93,14 +93,23 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
         fence_mbar_init();
     }
     if (warp == 1) { tmem_alloc(&sm.tmem_base, BN); tmem_relinquish(); }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.w);
+        for (int s = 0; s < p.n_src; ++s) tma_prefetch_desc(&maps.a[s]);
+    }
+    if (warp >= 2) {      // stage this CTA's bias slice (weights: independent of the preceding kernel)
+        const int t0 = threadIdx.x - 64;
+        for (int t = t0; t < BN; t += 128) sm.bias[t] = (n0 + t < p.cout) ? __ldg(p.bias + n0 + t) : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    pdl_wait();                    // inputs (and the split-K workspace) come from preceding kernels
+    pdl_launch_dependents();
 
     if (warp == 0) {
         if (lane == 0) {
-            tma_prefetch_desc(&maps.w);
             for (int s = 0; s < p.n_src; ++s) tma_prefetch_desc(&maps.a[s]);
             for (int it = 0; it < ksteps; ++it) {
                 const int kk = k_begin + it;
@@ -150,9 +159,6 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
         const bool pix_ok = (yo < p.Ho) && (xo < p.Wo);
         const size_t pix = ((size_t)b * p.Ho + yo) * p.Wo + xo;
         const size_t rpix = ((size_t)(p.residual_bcast ? 0 : b) * p.Ho + yo) * p.Wo + xo;
-        // overlap with the main loop: stage this CTA's bias slice in shared memory
-        for (int t = row; t < BN; t += 128) sm.bias[t] = (n0 + t < p.cout) ? __ldg(p.bias + n0 + t) : 0.f;
-        asm volatile("bar.sync 2, 128;" ::: "memory");
         mbar_wait(&sm.done, 0, 23);
         tc_fence_after();
         const int tile_lin = blockIdx.x * gridDim.y + blockIdx.y;
@@ -273,7 +279,7 @@ int launch_conv(const ConvMaps& maps, const ConvP& p, int cout_pad, cudaStream_t
         attr_done = true;
     }
     dim3 grid(p.tiles_x * p.tiles_y * p.batch, cout_pad / BN, p.splits);
-    conv_igemm_kernel<BN, STAGES><<<grid, 192, smem, stream>>>(maps, p);
+    XM_CHECK_CUDA(tc5_launch(conv_igemm_kernel<BN, STAGES>, grid, dim3(192), smem, stream, maps, p));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;

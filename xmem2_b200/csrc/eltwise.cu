@@ -11,7 +11,11 @@
 //   xm_upsample4x_aggregate  bilinear x4 + sigmoid + soft aggregation (modules.py:247, network.py:110-115, aggregate.py:6-16)
 //   xm_value_append       [hw,512] NHWC value -> [512][cap] column-major bank arena (kv_memory_store.py:70)
 #include "common.h"
+#include "tc5.cuh"
 #include <cuda_fp16.h>
+
+using tc5::pdl_wait;
+using tc5::pdl_launch_dependents;
 
 namespace {
 
@@ -22,6 +26,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 // channels: 0..2 image (shared by all b), 3 = mask[b], 4 = sum_{j!=b} mask[j]  (only when masks != null)
 __global__ void im2col_stem_kernel(const float* __restrict__ image, const float* __restrict__ masks, int n, int H, int W,
                                    int C, int kpad, __half* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
     // one thread = 8 consecutive k of one output pixel -> one 16-byte store (coalesced across the warp)
     const int Ho = H / 2, Wo = W / 2, K8 = kpad / 8;
     const size_t total = (size_t)n * Ho * Wo * K8;
@@ -63,6 +69,8 @@ __global__ void im2col_stem_kernel(const float* __restrict__ image, const float*
 
 // ---------------------------------------------------------------- maxpool 3x3 s2 p1 (8 channels / thread)
 __global__ void maxpool_kernel(const __half* __restrict__ in, int B, int H, int W, int C, int relu, __half* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
     const size_t total = (size_t)B * Ho * Wo * C8;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -97,6 +105,8 @@ __global__ void maxpool_kernel(const __half* __restrict__ in, int B, int H, int 
 }
 
 __global__ void relu_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n8) {
+    pdl_wait();
+    pdl_launch_dependents();
     const __half2 z = __float2half2_rn(0.f);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
         uint4 u = in[i];
@@ -112,6 +122,8 @@ __global__ void relu_kernel(const uint4* __restrict__ in, uint4* __restrict__ ou
 __global__ void keyproj_post_kernel(const __half* __restrict__ proj, int pstride, int hw, int hw_pad, __half* __restrict__ key,
                                     __half* __restrict__ sel, float* __restrict__ shr, __half* __restrict__ qp,
                                     float* __restrict__ bsq) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= hw_pad) return;
@@ -149,6 +161,8 @@ __global__ void keyproj_post_kernel(const __half* __restrict__ proj, int pstride
 // (a) per-(image, channel) partial sum and max over a slice of the pixels.  grid (C/64, B, CBAM_SLICES), block (64, 4)
 constexpr int CBAM_SLICES = 16;
 __global__ void cbam_pool_kernel(const __half* __restrict__ x, int HW, int C, float* __restrict__ psum, float* __restrict__ pmax) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float ssum[4][64], smax[4][64];
     const int c = blockIdx.x * 64 + threadIdx.x, b = blockIdx.y, sl = blockIdx.z;
     const int per = (HW + CBAM_SLICES - 1) / CBAM_SLICES;
@@ -170,6 +184,8 @@ __global__ void cbam_pool_kernel(const __half* __restrict__ x, int HW, int C, fl
 __global__ void cbam_mlp_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, int HW, const float* __restrict__ w1,
                                 const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int C,
                                 int R, float* __restrict__ scale) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ float sh[];          // [2][C] inputs, [2][R] hidden
     float* in0 = sh; float* in1 = sh + C; float* h0 = sh + 2 * C; float* h1 = h0 + R;
     const int b = blockIdx.x, t = threadIdx.x;
@@ -200,6 +216,8 @@ __global__ void cbam_mlp_kernel(const float* __restrict__ psum, const float* __r
 // (c) per pixel: max and mean over channels of x * scale_c.  One warp per pixel.
 __global__ void cbam_spatial_pool_kernel(const __half* __restrict__ x, const float* __restrict__ scale, int B, int HW, int C,
                                          float* __restrict__ comp) {
+    pdl_wait();
+    pdl_launch_dependents();
     const size_t pix = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (pix >= (size_t)B * HW) return;
@@ -217,6 +235,8 @@ __global__ void cbam_spatial_pool_kernel(const __half* __restrict__ x, const flo
 __global__ void cbam_apply_kernel(const __half* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ comp,
                                   const float* __restrict__ w7, float b7, int B, int H, int W, int C, __half* __restrict__ out,
                                   __half* __restrict__ out_relu) {
+    pdl_wait();
+    pdl_launch_dependents();
     const size_t pix = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (pix >= (size_t)B * H * W) return;
@@ -240,6 +260,8 @@ __global__ void cbam_apply_kernel(const __half* __restrict__ x, const float* __r
 // ---------------------------------------------------------------- bilinear x2 (align_corners=False) + broadcast skip
 __global__ void upsample2x_add_kernel(const __half* __restrict__ g, const __half* __restrict__ skip, int B, int h, int w, int C,
                                       __half* __restrict__ out, __half* __restrict__ out_relu) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int H = 2 * h, W = 2 * w, C2 = C / 2;
     const size_t total = (size_t)B * H * W * C2;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -271,6 +293,8 @@ __global__ void upsample2x_add_kernel(const __half* __restrict__ g, const __half
 // out[b][y][x][c] = mean over fxf of in; channel C (if extra) = mean of extra[b][.][.]; channels up to cpad are zero
 __global__ void area_down_kernel(const __half* __restrict__ in, const __half* __restrict__ extra, int B, int H, int W, int C,
                                  int f, int cpad, __half* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int Ho = H / f, Wo = W / f;
     const size_t total = (size_t)B * Ho * Wo * cpad;
     const float inv = 1.f / (f * f);
@@ -299,6 +323,8 @@ __global__ void area_down_kernel(const __half* __restrict__ in, const __half* __
 // ---------------------------------------------------------------- GRU (modules.py:68-72): h' = f*h*(1-u) + u*tanh(v)
 __global__ void gru_kernel(const __half* __restrict__ values, const float* __restrict__ h, size_t npix, int hd,
                            float* __restrict__ h_out, __half* __restrict__ h_out16) {
+    pdl_wait();
+    pdl_launch_dependents();
     const size_t total = npix * hd;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t p = i / hd; const int c = i % hd;
@@ -316,6 +342,8 @@ __global__ void gru_kernel(const __half* __restrict__ values, const float* __res
 // logits4 [n][h4][w4] fp16 -> prob [n+1][H][W] fp32 (and logits) with H=4*h4.
 __global__ void upsample4x_aggregate_kernel(const __half* __restrict__ l4, int n, int h4, int w4, float* __restrict__ prob,
                                             float* __restrict__ logits_out) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int H = 4 * h4, W = 4 * w4;
     const size_t total = (size_t)H * W;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -350,6 +378,8 @@ __global__ void upsample4x_aggregate_kernel(const __half* __restrict__ l4, int n
 
 // ---------------------------------------------------------------- value [n][hw][512] -> arena [obj][512][cap] at column col0
 __global__ void value_append_kernel(const __half* __restrict__ val, int hw, int cap, int col0, __half* __restrict__ arena) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ __half tile[32][34];
     const int o = blockIdx.z;
     const int q0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -379,7 +409,7 @@ extern "C" int xm_im2col_stem(const float* image, const float* masks, int32_t n,
     const int C = masks ? 5 : 3;
     XM_REQUIRE(kpad >= 49 * C && kpad % 64 == 0, "xm_im2col_stem: kpad must be a multiple of 64 >= %d", 49 * C);
     const size_t total = (size_t)n * (H / 2) * (W / 2) * (kpad / 8);
-    im2col_stem_kernel<<<grid_for(total), 256, 0, STREAM>>>(image, masks, n, H, W, C, kpad, (__half*)out);
+    XM_CHECK_CUDA(tc5_launch(im2col_stem_kernel, dim3(grid_for(total)), dim3(256), 0, STREAM, image, masks, n, H, W, C, kpad, (__half*)out));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
@@ -388,7 +418,7 @@ extern "C" int xm_im2col_stem(const float* image, const float* masks, int32_t n,
 extern "C" int xm_maxpool3x3s2(const void* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t relu, void* out, void* stream) {
     XM_REQUIRE(in && out && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "xm_maxpool3x3s2: bad arguments");
     const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
-    maxpool_kernel<<<grid_for(total), 256, 0, STREAM>>>((const __half*)in, B, H, W, C, relu, (__half*)out);
+    XM_CHECK_CUDA(tc5_launch(maxpool_kernel, dim3(grid_for(total)), dim3(256), 0, STREAM, (const __half*)in, B, H, W, C, relu, (__half*)out));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
@@ -396,7 +426,7 @@ extern "C" int xm_maxpool3x3s2(const void* in, int32_t B, int32_t H, int32_t W, 
 
 extern "C" int xm_relu(const void* in, void* out, int64_t n, void* stream) {
     XM_REQUIRE(in && out && n % 8 == 0, "xm_relu: n must be a multiple of 8");
-    relu_kernel<<<grid_for(n / 8), 256, 0, STREAM>>>((const uint4*)in, (uint4*)out, (size_t)n / 8);
+    XM_CHECK_CUDA(tc5_launch(relu_kernel, dim3(grid_for(n / 8)), dim3(256), 0, STREAM, (const uint4*)in, (uint4*)out, (size_t)n / 8));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
@@ -406,8 +436,8 @@ extern "C" int xm_keyproj_post(const void* proj, int32_t pstride, int32_t hw, in
                                void* qp, float* bsq, void* stream) {
     XM_REQUIRE(proj && key && sel && shr && pstride >= 129 && hw > 0 && hw_pad >= hw, "xm_keyproj_post: bad arguments");
     const int rows = qp ? hw_pad : hw;
-    keyproj_post_kernel<<<(rows + 7) / 8, 256, 0, STREAM>>>((const __half*)proj, pstride, hw, rows, (__half*)key, (__half*)sel, shr,
-                                                            (__half*)qp, bsq);
+    XM_CHECK_CUDA(tc5_launch(keyproj_post_kernel, dim3((rows + 7) / 8), dim3(256), 0, STREAM, (const __half*)proj, pstride, hw, rows, (__half*)key, (__half*)sel, shr,
+                                                            (__half*)qp, bsq));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
@@ -420,12 +450,12 @@ extern "C" int xm_cbam(const void* x, int32_t B, int32_t H, int32_t W, int32_t C
     const int HW = H * W, R = C / 16;
     float* avg = scratch; float* mx = avg + (size_t)B * CBAM_SLICES * C; float* scale = mx + (size_t)B * CBAM_SLICES * C;
     float* comp = scale + (size_t)B * C;
-    cbam_pool_kernel<<<dim3(C / 64, B, CBAM_SLICES), dim3(64, 4), 0, STREAM>>>((const __half*)x, HW, C, avg, mx);
-    cbam_mlp_kernel<<<B, C, (2 * C + 2 * R) * sizeof(float), STREAM>>>(avg, mx, HW, w1, b1, w2, b2, C, R, scale);
+    XM_CHECK_CUDA(tc5_launch(cbam_pool_kernel, dim3(dim3(C / 64, B, CBAM_SLICES)), dim3(dim3(64, 4)), 0, STREAM, (const __half*)x, HW, C, avg, mx));
+    XM_CHECK_CUDA(tc5_launch(cbam_mlp_kernel, dim3(B), dim3(C), (2 * C + 2 * R) * sizeof(float), STREAM, avg, mx, HW, w1, b1, w2, b2, C, R, scale));
     const size_t npix = (size_t)B * HW;
-    cbam_spatial_pool_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, STREAM>>>((const __half*)x, scale, B, HW, C, comp);
-    cbam_apply_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, STREAM>>>((const __half*)x, scale, comp, w7, b7, B, H, W, C, (__half*)out,
-                                                                     (__half*)out_relu);
+    XM_CHECK_CUDA(tc5_launch(cbam_spatial_pool_kernel, dim3((unsigned)((npix + 7) / 8)), dim3(256), 0, STREAM, (const __half*)x, scale, B, HW, C, comp));
+    XM_CHECK_CUDA(tc5_launch(cbam_apply_kernel, dim3((unsigned)((npix + 7) / 8)), dim3(256), 0, STREAM, (const __half*)x, scale, comp, w7, b7, B, H, W, C, (__half*)out,
+                                                                     (__half*)out_relu));
     xm_count_launches(3);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
@@ -435,8 +465,8 @@ extern "C" int xm_upsample2x_add(const void* g, const void* skip, int32_t B, int
                                  void* stream) {
     XM_REQUIRE(g && skip && out && C % 2 == 0, "xm_upsample2x_add: bad arguments");
     const size_t total = (size_t)B * 4 * h * w * (C / 2);
-    upsample2x_add_kernel<<<grid_for(total), 256, 0, STREAM>>>((const __half*)g, (const __half*)skip, B, h, w, C, (__half*)out,
-                                                               (__half*)out_relu);
+    XM_CHECK_CUDA(tc5_launch(upsample2x_add_kernel, dim3(grid_for(total)), dim3(256), 0, STREAM, (const __half*)g, (const __half*)skip, B, h, w, C, (__half*)out,
+                                                               (__half*)out_relu));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
@@ -446,7 +476,7 @@ extern "C" int xm_area_down(const void* in, const void* extra, int32_t B, int32_
                             void* out, void* stream) {
     XM_REQUIRE(in && out && f >= 1 && H % f == 0 && W % f == 0 && cpad >= C + (extra ? 1 : 0), "xm_area_down: bad arguments");
     const size_t total = (size_t)B * (H / f) * (W / f) * cpad;
-    area_down_kernel<<<grid_for(total), 256, 0, STREAM>>>((const __half*)in, (const __half*)extra, B, H, W, C, f, cpad, (__half*)out);
+    XM_CHECK_CUDA(tc5_launch(area_down_kernel, dim3(grid_for(total)), dim3(256), 0, STREAM, (const __half*)in, (const __half*)extra, B, H, W, C, f, cpad, (__half*)out));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
@@ -454,8 +484,8 @@ extern "C" int xm_area_down(const void* in, const void* extra, int32_t B, int32_
 
 extern "C" int xm_gru(const void* values, const float* h, int64_t npix, int32_t hidden_dim, float* h_out, void* h_out16, void* stream) {
     XM_REQUIRE(values && h && h_out && h_out16 && npix > 0, "xm_gru: bad arguments");
-    gru_kernel<<<grid_for((size_t)npix * hidden_dim), 256, 0, STREAM>>>((const __half*)values, h, (size_t)npix, hidden_dim, h_out,
-                                                                      (__half*)h_out16);
+    XM_CHECK_CUDA(tc5_launch(gru_kernel, dim3(grid_for((size_t)npix * hidden_dim)), dim3(256), 0, STREAM, (const __half*)values, h, (size_t)npix, hidden_dim, h_out,
+                                                                      (__half*)h_out16));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
@@ -463,7 +493,7 @@ extern "C" int xm_gru(const void* values, const float* h, int64_t npix, int32_t 
 
 extern "C" int xm_upsample4x_aggregate(const void* logits4, int32_t n, int32_t h4, int32_t w4, float* prob, float* logits, void* stream) {
     XM_REQUIRE(logits4 && prob && n >= 1 && n <= XM_MAX_GROUPS * 4, "xm_upsample4x_aggregate: bad arguments");
-    upsample4x_aggregate_kernel<<<grid_for((size_t)16 * h4 * w4), 256, 0, STREAM>>>((const __half*)logits4, n, h4, w4, prob, logits);
+    XM_CHECK_CUDA(tc5_launch(upsample4x_aggregate_kernel, dim3(grid_for((size_t)16 * h4 * w4)), dim3(256), 0, STREAM, (const __half*)logits4, n, h4, w4, prob, logits));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
@@ -471,8 +501,8 @@ extern "C" int xm_upsample4x_aggregate(const void* logits4, int32_t n, int32_t h
 
 extern "C" int xm_value_append(const void* value_hwc, int32_t n_obj, int32_t hw, void* arena, int64_t cap, int32_t col0, void* stream) {
     XM_REQUIRE(value_hwc && arena && n_obj >= 1 && hw > 0 && col0 >= 0 && col0 + hw <= cap, "xm_value_append: bad arguments");
-    value_append_kernel<<<dim3((hw + 31) / 32, XM_CV / 32, n_obj), dim3(32, 8), 0, STREAM>>>((const __half*)value_hwc, hw, (int)cap, col0,
-                                                                                           (__half*)arena);
+    XM_CHECK_CUDA(tc5_launch(value_append_kernel, dim3(dim3((hw + 31) / 32, XM_CV / 32, n_obj)), dim3(dim3(32, 8)), 0, STREAM, (const __half*)value_hwc, hw, (int)cap, col0,
+                                                                                           (__half*)arena));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;

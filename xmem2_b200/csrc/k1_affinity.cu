@@ -83,6 +83,8 @@ __device__ __forceinline__ float fast_exp(float x) {
 // ---------------------------------------------------------------------------------------------
 __global__ void query_pack_kernel(const __half* __restrict__ key, const __half* __restrict__ sel, int hw, int hw_pad,
                                   __half* __restrict__ qp, float* __restrict__ bsq) {
+    pdl_wait();
+    pdl_launch_dependents();
     // one warp per query row; lane handles channels lane, lane+32
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
@@ -108,6 +110,8 @@ __global__ void query_pack_kernel(const __half* __restrict__ key, const __half* 
 }
 
 __global__ void key_pack_kernel(const __half* __restrict__ key, int n, __half* __restrict__ dst) {
+    pdl_wait();
+    pdl_launch_dependents();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * XM_CK) return;
     int row = i / XM_CK, c = i % XM_CK;
@@ -154,6 +158,8 @@ k1_scan(const __grid_constant__ K1Maps maps, const K1Seg* __restrict__ sgp, cons
     extern __shared__ uint8_t smem_raw[];
     ScanSmem& sm = *reinterpret_cast<ScanSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ K1Seg sg;                       // column-range table lives in device memory (CUDA-graph friendly)
+    pdl_wait();
+    pdl_launch_dependents();
     if (threadIdx.x < sizeof(K1Seg) / 4) reinterpret_cast<uint32_t*>(&sg)[threadIdx.x] = reinterpret_cast<const uint32_t*>(sgp)[threadIdx.x];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -326,6 +332,8 @@ k1_scan(const __grid_constant__ K1Maps maps, const K1Seg* __restrict__ sgp, cons
 // want_den: also 1 / sum_topk exp(S)  (do_softmax top-k branch, memory_util.py:48-49: no max subtraction)
 __global__ void k1_topk_merge(const float* __restrict__ cand, int nlists, int hw, int hw_pad, int top_k, int want_den,
                               float* __restrict__ tau, float* __restrict__ inv_den) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (q >= hw_pad) return;
@@ -396,6 +404,8 @@ k1_readout_pass2(const __grid_constant__ K1Maps maps, const K1Seg* __restrict__ 
     extern __shared__ uint8_t smem_raw[];
     P2Smem& sm = *reinterpret_cast<P2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ K1Seg sg;
+    pdl_wait();
+    pdl_launch_dependents();
     if (threadIdx.x < sizeof(K1Seg) / 4) reinterpret_cast<uint32_t*>(&sg)[threadIdx.x] = reinterpret_cast<const uint32_t*>(sgp)[threadIdx.x];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -600,6 +610,8 @@ k1_readout_pass2(const __grid_constant__ K1Maps maps, const K1Seg* __restrict__ 
 // sum the column slices, convert to fp16, write CHW and/or HWC
 __global__ void k1_finish(const float* __restrict__ partial, int nsplit, int n_obj, int hw, int hw_pad, int obj_begin,
                           __half* __restrict__ out_chw, __half* __restrict__ out_hwc) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float tile[32][33];
     const int o = blockIdx.z;
     const int c0 = blockIdx.y * 32, q0 = blockIdx.x * 32;
@@ -633,8 +645,8 @@ extern "C" int xm_query_pack(const void* key_hwc, const void* sel_hwc, int32_t h
     XM_REQUIRE(key_hwc && sel_hwc && qp && bsq, "xm_query_pack: null pointer");
     XM_REQUIRE(hw > 0 && hw_pad >= hw && hw_pad % TQ == 0, "xm_query_pack: hw_pad must be a multiple of 128 and >= hw");
     const int warps = 8;
-    query_pack_kernel<<<(hw_pad + warps - 1) / warps, warps * 32, 0, (cudaStream_t)stream>>>(
-        (const __half*)key_hwc, (const __half*)sel_hwc, hw, hw_pad, (__half*)qp, bsq);
+    XM_CHECK_CUDA(tc5_launch(query_pack_kernel, dim3((hw_pad + warps - 1) / warps), dim3(warps * 32), 0, (cudaStream_t)stream,
+                             (const __half*)key_hwc, (const __half*)sel_hwc, hw, hw_pad, (__half*)qp, bsq));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
@@ -644,7 +656,7 @@ extern "C" int xm_key_pack(const void* key_hwc, int32_t n, void* dst_rows, void*
     XM_REQUIRE(key_hwc && dst_rows && n >= 0, "xm_key_pack: bad arguments");
     if (n == 0) return XM_OK;
     const int total = n * XM_CK;
-    key_pack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const __half*)key_hwc, n, (__half*)dst_rows);
+    XM_CHECK_CUDA(tc5_launch(key_pack_kernel, dim3((total + 255) / 256), dim3(256), 0, (cudaStream_t)stream, (const __half*)key_hwc, n, (__half*)dst_rows));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
@@ -775,15 +787,17 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
         XM_REQUIRE(gr.n_obj > 0 && gr.obj_begin >= 0 && gr.obj_begin + gr.n_obj <= a->n_obj_total, "xm_affinity_readout: bad group %d objects", g);
         const K1Seg* sgp = plan_dev + g;
         // scan A (slot maxima) -> tau_lo ; scan B (collect > pred(tau_lo)) -> tau, 1/den
-        k1_scan<MODE_SLOTMAX><<<dim3(qtiles, nsplit1), SCAN_THREADS, sizeof(ScanSmem) + 1024, stream>>>(
-            maps, sgp, a->bsq, nullptr, hw_pad, cand, g == 0 ? a->debug_scores : nullptr);
+        XM_CHECK_CUDA(tc5_launch(k1_scan<MODE_SLOTMAX>, dim3(qtiles, nsplit1), dim3(SCAN_THREADS), sizeof(ScanSmem) + 1024, stream,
+                                 maps, sgp, a->bsq, (const float*)nullptr, hw_pad, cand, g == 0 ? a->debug_scores : (float*)nullptr));
         XM_CHECK_CUDA(cudaGetLastError());
-        k1_topk_merge<<<(hw_pad + 3) / 4, 128, 0, stream>>>(cand, nsplit1 * 2, hw, hw_pad, a->top_k, 0, tau_lo, nullptr);
+        XM_CHECK_CUDA(tc5_launch(k1_topk_merge, dim3((hw_pad + 3) / 4), dim3(128), 0, stream, (const float*)cand, nsplit1 * 2, hw, hw_pad,
+                                 a->top_k, 0, tau_lo, (float*)nullptr));
         XM_CHECK_CUDA(cudaGetLastError());
-        k1_scan<MODE_COLLECT><<<dim3(qtiles, nsplit1), SCAN_THREADS, sizeof(ScanSmem) + 1024, stream>>>(
-            maps, sgp, a->bsq, tau_lo, hw_pad, cand, nullptr);
+        XM_CHECK_CUDA(tc5_launch(k1_scan<MODE_COLLECT>, dim3(qtiles, nsplit1), dim3(SCAN_THREADS), sizeof(ScanSmem) + 1024, stream,
+                                 maps, sgp, a->bsq, (const float*)tau_lo, hw_pad, cand, (float*)nullptr));
         XM_CHECK_CUDA(cudaGetLastError());
-        k1_topk_merge<<<(hw_pad + 3) / 4, 128, 0, stream>>>(cand, nsplit1 * 2, hw, hw_pad, a->top_k, 1, tau, inv_den);
+        XM_CHECK_CUDA(tc5_launch(k1_topk_merge, dim3((hw_pad + 3) / 4), dim3(128), 0, stream, (const float*)cand, nsplit1 * 2, hw, hw_pad,
+                                 a->top_k, 1, tau, inv_den));
         XM_CHECK_CUDA(cudaGetLastError());
 
         // pass 2
@@ -791,12 +805,12 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
         int nsplit2 = sms / ctas_per_slice;               // one wave
         nsplit2 = nsplit2 < 1 ? 1 : nsplit2;
         if (nsplit2 > K1_MAX_SPLIT) nsplit2 = K1_MAX_SPLIT;
-        k1_readout_pass2<<<dim3(qtiles, 2 * gr.n_obj, nsplit2), SCAN_THREADS, sizeof(P2Smem) + 1024, stream>>>(
-            maps, sgp, a->bsq, tau, inv_den, hw_pad, gr.obj_begin, gr.n_obj, g == 0 ? 1 : 0, partial);
+        XM_CHECK_CUDA(tc5_launch(k1_readout_pass2, dim3(qtiles, 2 * gr.n_obj, nsplit2), dim3(SCAN_THREADS), sizeof(P2Smem) + 1024, stream,
+                                 maps, sgp, a->bsq, (const float*)tau, (const float*)inv_den, hw_pad, gr.obj_begin, gr.n_obj, g == 0 ? 1 : 0, partial));
         XM_CHECK_CUDA(cudaGetLastError());
         xm_count_launches(6);
-        k1_finish<<<dim3((hw + 31) / 32, XM_CV / 32, gr.n_obj), dim3(32, 8), 0, stream>>>(
-            partial, nsplit2, gr.n_obj, hw, hw_pad, gr.obj_begin, (__half*)a->readout_chw, (__half*)a->readout_hwc);
+        XM_CHECK_CUDA(tc5_launch(k1_finish, dim3((hw + 31) / 32, XM_CV / 32, gr.n_obj), dim3(32, 8), 0, stream,
+                                 (const float*)partial, nsplit2, gr.n_obj, hw, hw_pad, gr.obj_begin, (__half*)a->readout_chw, (__half*)a->readout_hwc));
         XM_CHECK_CUDA(cudaGetLastError());
     }
     return XM_OK;

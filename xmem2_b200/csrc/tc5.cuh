@@ -14,6 +14,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of this library is launched with programmatic stream serialization: its prologue (barrier init,
+// TMEM allocation, descriptor prefetch) may overlap the tail of the preceding kernel; pdl_wait() blocks until the
+// preceding grids have completed and their writes are visible, so it must precede the first dependent global access.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -160,6 +167,19 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 }
 
 }  // namespace tc5
+
+// host: launch with the PDL attribute (xm_pdl_enabled() == 0 falls back to a plain launch)
+int xm_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t tc5_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = xm_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // host: point this translation unit's trap buffer at the shared host-mapped page (common.cu)
 int* xm_debug_trap_device_ptr();
