@@ -226,13 +226,14 @@ def main():
     torch.cuda.set_device(local)
     device = f'cuda:{local}'
     from xmem2_b200 import lib
+    from xmem2_b200.util import dist as xd
     from xmem2_b200.inference.inference_core import InferenceCore
     from xmem2_b200.model.network import XMem
     from xmem2_b200.util.synth import synth_state_dict
     lib.load()
     net = XMem(dict(CFG), None).to(device).eval()
     net.load_weights(synth_state_dict(0))
-    frames_h, masks_h = clip_inputs(1234 + 1000 * rank)
+    frames_h, masks_h = clip_inputs(xd.stream_seed(1234, rank))
     frames_pin = frames_h.pin_memory(); masks_pin = {k: v.pin_memory() for k, v in masks_h.items()}
     frames_d = frames_h.to(device); masks_d = {k: v.to(device) for k, v in masks_h.items()}
     factory = lambda: InferenceCore(net, dict(CFG))
@@ -254,10 +255,8 @@ def main():
             run_clip(factory, fr, mk, device, host_io)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms = xd.max_over_ranks(e0.elapsed_time(e1), device)          # the slowest rank's device time
         launches = lib.load().xm_launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], device=device); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
         return ms, launches
 
     with ClockSampler(local) as clk:

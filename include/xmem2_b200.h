@@ -38,6 +38,7 @@ int xm_version(void);
 int xm_debug_last_trap(int* out7);
 /* number of kernels this library has launched so far (accounting for bench.py) */
 long long xm_launch_count(void);
+void xm_add_launch_count(int n);   /* the host mirror reports kernels it replays from a recorded CUDA graph */
 /* programmatic dependent launch between this library's kernels (default on) */
 void xm_set_pdl(int on);
 

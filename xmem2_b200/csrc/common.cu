@@ -99,6 +99,7 @@ extern "C" int xm_debug_last_trap(int* out) {
 static std::atomic<long long> g_launches{0};
 void xm_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 extern "C" long long xm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" void xm_add_launch_count(int n) { xm_count_launches(n); }   // kernels replayed from a recorded CUDA graph
 
 // ---- programmatic dependent launch toggle (default on; XMEM_NO_PDL=1 or xm_set_pdl(0) turns it off) ----
 #include <cstdlib>

@@ -13,6 +13,7 @@ import time
 
 import torch
 
+from .. import lib
 from ..model.aggregate import aggregate
 from ..model.network import XMem
 from ..util.tensor_util import pad_divide_by, unpad
@@ -163,6 +164,7 @@ class InferenceCore:
         h, w = image.shape[-2] // 16, image.shape[-1] // 16
         mem.upload_plan(h * w, image.device)
         self._graph.replay()
+        lib.load().xm_add_launch_count(self._graph_launches)
         return self._g_prob
 
     def _capture(self, image, sig):
@@ -178,6 +180,7 @@ class InferenceCore:
         mem.upload_plan(h * w, dev)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
+        launches0 = lib.load().xm_launch_count()
         with torch.cuda.graph(graph):
             key, _, selection, f16, f8, f4 = net.encode_key(self._g_image, need_ek=True, need_sk=True)
             readout = mem.match_memory(key, selection).unsqueeze(0)
@@ -185,6 +188,8 @@ class InferenceCore:
             self._g_hidden.copy_(hidden)
             self._g_prob = prob[0]
         self._graph, self._graph_sig = graph, sig
+        self._graph_launches = int(lib.load().xm_launch_count() - launches0)     # recorded, not executed
+        lib.load().xm_add_launch_count(-self._graph_launches)
         if os.environ.get('XMEM_TRACE'):
             torch.cuda.synchronize(dev)
             print(f'[xmem2_b200] recorded frame graph in {time.perf_counter() - t0:.3f}s', flush=True)

@@ -82,6 +82,7 @@ def load() -> C.CDLL:
         vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
         lib.xm_debug_last_trap.argtypes = [C.POINTER(C.c_int)]
         lib.xm_launch_count.restype = C.c_longlong
+        lib.xm_add_launch_count.argtypes = [C.c_int]
         lib.xm_im2col_stem.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
         lib.xm_maxpool3x3s2.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
         lib.xm_relu.argtypes = [vp, vp, i64, vp]
