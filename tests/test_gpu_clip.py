@@ -95,3 +95,42 @@ def test_disable_memory_updates_does_not_advance_state(net):
     assert core.curr_ti == ti and core.memory.permanent_work_mem.size == use
     assert torch.equal(core.memory.get_hidden(), hidden)
     assert torch.isfinite(p).all() and abs(p.sum(0).mean().item() - 1.0) < 1e-3
+
+
+def test_two_interleaved_cores_share_one_recorded_graph_without_crosstalk(net):
+    # two videos processed alternately on one network (the recorded frame graph and its static buffers are shared):
+    # each must produce exactly what it produces when run alone
+    dev = 'cuda'
+    H, W = 96, 128
+
+    def run(seed_shift, other=None):
+        core = InferenceCore(net, dict(BASE))
+        core.set_all_labels([1])
+        f = lambda ti: synth_frame(ti + seed_shift, H, W, structured=True).to(dev)
+        core.put_to_permanent_memory(f(0), synth_mask(0, H, W, 1).to(dev))
+        core.step(f(0), synth_mask(0, H, W, 1).to(dev), [1], do_not_add_mask_to_memory=True)
+        outs = []
+        for ti in range(1, 8):
+            outs.append(core.step(f(ti)).clone())
+            if other is not None:
+                other()
+        return outs
+
+    alone = run(0)
+    # a second core that advances one frame every time the first one does
+    state = {}
+
+    def make_other():
+        core = InferenceCore(net, dict(BASE))
+        core.set_all_labels([1])
+        g = lambda ti: synth_frame(ti + 50, H, W, structured=True).to(dev)
+        core.put_to_permanent_memory(g(0), synth_mask(3, H, W, 1).to(dev))
+        core.step(g(0), synth_mask(3, H, W, 1).to(dev), [1], do_not_add_mask_to_memory=True)
+        state['ti'] = 1
+        def advance():
+            core.step(g(state['ti'])); state['ti'] += 1
+        return advance
+
+    mixed = run(0, other=make_other())
+    for a, b in zip(alone, mixed):
+        assert torch.equal(a, b)

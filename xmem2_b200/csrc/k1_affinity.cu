@@ -762,7 +762,7 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
     }
     for (int i = 0; i < 3; ++i) {
         const xm_bank_t& bk = a->banks[i];
-        if (bk.size <= 0 || !bk.keys) {     // unused bank: alias the query map so the struct is fully initialised
+        if (!bk.keys || bk.cap <= 0) {      // bank without an arena: alias the query map so the struct is fully initialised
             maps.k[i] = maps.q;
             maps.v[i] = maps.q;
             continue;

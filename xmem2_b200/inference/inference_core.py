@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import os
 import time
+import weakref
 
 import torch
 
@@ -18,6 +19,13 @@ from ..model.aggregate import aggregate
 from ..model.network import XMem
 from ..util.tensor_util import pad_divide_by, unpad
 from .memory_manager import MemoryManager
+
+
+# recorded frame graphs are shared by every InferenceCore built on the same network (one per video in the reference
+# driver): key = (id(network), signature); value = graph + its static buffers.  Arena recycling in KeyValueMemoryStore
+# makes consecutive videos of the same shape hit the same signature.
+_GRAPH_CACHE = {}
+_GRAPH_CACHE_MAX = 8
 
 
 class InferenceCore:
@@ -151,11 +159,28 @@ class InferenceCore:
         mem = self.memory
         sig = (tuple(image.shape), mem.layout_signature(), len(self.all_labels))
         if self._graph is None or self._graph_sig != sig:
-            if self._graph_warm_sig != sig:
-                self._graph_warm_sig = sig          # run this frame eagerly, record on the next one
-                self._graph = None
-                return None
-            self._capture(image, sig)
+            cached = _GRAPH_CACHE.get((id(self.network), sig))
+            if cached is not None:
+                self._graph, self._g_image, self._g_hidden, self._g_prob, self._graph_launches, self._g_owner = cached
+                self._graph_sig = sig
+            else:
+                if self._graph_warm_sig != sig:
+                    self._graph_warm_sig = sig          # run this frame eagerly, record on the next one
+                    self._graph = None
+                    return None
+                self._capture(image, sig)
+                if len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
+                    _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
+                self._g_owner = [None]
+                _GRAPH_CACHE[(id(self.network), sig)] = (self._graph, self._g_image, self._g_hidden, self._g_prob,
+                                                         self._graph_launches, self._g_owner)
+        # the graph's hidden-state buffer is shared by every core using this graph: hand the previous user its own copy
+        prev = self._g_owner[0]() if self._g_owner[0] is not None else None
+        if prev is not None and prev is not self:
+            ph = prev.memory.get_hidden()
+            if ph is not None and ph.data_ptr() == self._g_hidden.data_ptr():
+                prev.memory.set_hidden(ph.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3))
+        self._g_owner[0] = weakref.ref(self)
         hid = mem.get_hidden()
         if hid.data_ptr() != self._g_hidden.data_ptr():
             self._g_hidden.copy_(hid)

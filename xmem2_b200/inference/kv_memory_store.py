@@ -30,6 +30,12 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+# Arenas of finished videos are recycled: a serving process handles many clips, and re-using the same device
+# addresses lets InferenceCore re-use its recorded CUDA graphs (their kernels have the arena addresses baked in).
+_ARENA_POOL = {}
+_ARENA_POOL_MAX = 8
+
+
 class KeyValueMemoryStore:
     def __init__(self, count_usage: bool, reserve: int = 0, right_aligned_groups: bool = False):
         self.count_usage = count_usage
@@ -50,19 +56,38 @@ class KeyValueMemoryStore:
     # ------------------------------------------------------------------ arena management
     def _alloc(self, cap, n_obj, device):
         cap = _round_up(max(cap, 64), 64)
-        kp = torch.zeros((cap, 2 * CK), dtype=torch.float16, device=device)
-        s = torch.ones((cap,), dtype=torch.float32, device=device)
-        e = torch.zeros((cap, CK), dtype=torch.float16, device=device)
-        v = torch.zeros((max(n_obj, 1), CV, cap), dtype=torch.float16, device=device)
-        use = torch.zeros((cap,), dtype=torch.float32, device=device)
-        life = torch.zeros((cap,), dtype=torch.float32, device=device)
+        pooled = _ARENA_POOL.get((str(device), cap, max(n_obj, 1)))
+        if pooled:
+            kp, s, e, v, use, life = pooled.pop()        # stale contents are finite and masked by `size`
+        else:
+            kp = torch.zeros((cap, 2 * CK), dtype=torch.float16, device=device)
+            s = torch.ones((cap,), dtype=torch.float32, device=device)
+            e = torch.zeros((cap, CK), dtype=torch.float16, device=device)
+            v = torch.zeros((max(n_obj, 1), CV, cap), dtype=torch.float16, device=device)
+            use = torch.zeros((cap,), dtype=torch.float32, device=device)
+            life = torch.zeros((cap,), dtype=torch.float32, device=device)
         if self._kp is not None and self._n > 0:
             n = self._n
             kp[:n] = self._kp[:n]; s[:n] = self._s[:n]; e[:n] = self._e[:n]
             v[:self._v.shape[0], :, :n] = self._v[:, :, :n]
             use[:n] = self._use[:n]; life[:n] = self._life[:n]
+        self._release()
         self._kp, self._s, self._e, self._v, self._use, self._life = kp, s, e, v, use, life
         self._cap, self._dev = cap, device
+
+    def _release(self):
+        if self._kp is not None:
+            key = (str(self._dev), self._cap, self._v.shape[0])
+            lst = _ARENA_POOL.setdefault(key, [])
+            if len(lst) < _ARENA_POOL_MAX:
+                lst.append((self._kp, self._s, self._e, self._v, self._use, self._life))
+            self._kp = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
 
     def _ensure(self, extra_cols, n_obj, device):
         need = self._n + extra_cols
@@ -312,7 +337,7 @@ class KeyValueMemoryStore:
     # ------------------------------------------------------------------ kernel-side description
     def bank_struct(self, bank, with_usage: bool):
         """fill an XmBank (include/xmem2_b200.h) for the fused read kernel."""
-        if not self._engaged or self._n == 0:
+        if self._kp is None:
             bank.size = 0
             bank.keys = None
             return
