@@ -144,6 +144,8 @@ int xm_cbam(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, const flo
 int xm_upsample2x_add(const void* g, const void* skip, int32_t B, int32_t h, int32_t w, int32_t C, void* out, void* out_relu, void* stream);
 /* area (mean) down-sampling by f; optional extra single-channel map appended as channel C; zero padded to cpad */
 int xm_area_down(const void* in, const void* extra, int32_t B, int32_t H, int32_t W, int32_t C, int32_t f, int32_t cpad, void* out, void* stream);
+/* 3x3, pad 1, ONE output channel (decoder.pred, model/modules.py:227,239): weight fp16 [9][C], out fp16 [B][H][W] */
+int xm_conv3x3_c1(const void* in, const void* weight_tap_c, float bias, int32_t B, int32_t H, int32_t W, int32_t C, void* out, void* stream);
 /* values fp16 [npix][3*hd], h fp32 [npix][hd] -> h' = f*h*(1-u) + u*tanh(v) (modules.py:68-72) as fp32 and fp16 */
 int xm_gru(const void* values, const float* h, int64_t npix, int32_t hidden_dim, float* h_out, void* h_out16, void* stream);
 /* logits4 fp16 [n][h4][w4] -> bilinear x4, sigmoid, soft aggregation: prob/logits fp32 [n+1][4*h4][4*w4]  */

@@ -258,15 +258,16 @@ __global__ void cbam_apply_kernel(const __half* __restrict__ x, const float* __r
 }
 
 // ---------------------------------------------------------------- bilinear x2 (align_corners=False) + broadcast skip
+// 8 channels (16 bytes) per thread
 __global__ void upsample2x_add_kernel(const __half* __restrict__ g, const __half* __restrict__ skip, int B, int h, int w, int C,
                                       __half* __restrict__ out, __half* __restrict__ out_relu) {
     pdl_wait();
     pdl_launch_dependents();
-    const int H = 2 * h, W = 2 * w, C2 = C / 2;
-    const size_t total = (size_t)B * H * W * C2;
+    const int H = 2 * h, W = 2 * w, C8 = C / 8;
+    const size_t total = (size_t)B * H * W * C8;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c2 = i % C2;
-        size_t p = i / C2;
+        const int c8 = i % C8;
+        size_t p = i / C8;
         const int x = p % W; p /= W;
         const int y = p % H;
         const int b = p / H;
@@ -274,49 +275,102 @@ __global__ void upsample2x_add_kernel(const __half* __restrict__ g, const __half
         const int y0 = (int)sy, x0 = (int)sx;
         const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
         const float fy = sy - y0, fx = sx - x0;
-        const __half2* gb = reinterpret_cast<const __half2*>(g) + (size_t)b * h * w * C2;
-        const float2 v00 = __half22float2(gb[((size_t)y0 * w + x0) * C2 + c2]);
-        const float2 v01 = __half22float2(gb[((size_t)y0 * w + x1) * C2 + c2]);
-        const float2 v10 = __half22float2(gb[((size_t)y1 * w + x0) * C2 + c2]);
-        const float2 v11 = __half22float2(gb[((size_t)y1 * w + x1) * C2 + c2]);
-        const float2 sk = __half22float2(reinterpret_cast<const __half2*>(skip)[((size_t)y * W + x) * C2 + c2]);
-        // the reference rounds the interpolated map to fp16 before the add (F.interpolate under autocast)
-        float rx = (1.f - fy) * ((1.f - fx) * v00.x + fx * v01.x) + fy * ((1.f - fx) * v10.x + fx * v11.x);
-        float ry = (1.f - fy) * ((1.f - fx) * v00.y + fx * v01.y) + fy * ((1.f - fx) * v10.y + fx * v11.y);
-        rx += sk.x; ry += sk.y;
-        reinterpret_cast<__half2*>(out)[i] = __floats2half2_rn(rx, ry);
-        if (out_relu) reinterpret_cast<__half2*>(out_relu)[i] = __floats2half2_rn(fmaxf(rx, 0.f), fmaxf(ry, 0.f));
+        const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+        const uint4* gb = reinterpret_cast<const uint4*>(g) + (size_t)b * h * w * C8;
+        const uint4 a00 = __ldg(gb + ((size_t)y0 * w + x0) * C8 + c8), a01 = __ldg(gb + ((size_t)y0 * w + x1) * C8 + c8);
+        const uint4 a10 = __ldg(gb + ((size_t)y1 * w + x0) * C8 + c8), a11 = __ldg(gb + ((size_t)y1 * w + x1) * C8 + c8);
+        const uint4 sk = __ldg(reinterpret_cast<const uint4*>(skip) + ((size_t)y * W + x) * C8 + c8);
+        const __half2* h00 = reinterpret_cast<const __half2*>(&a00); const __half2* h01 = reinterpret_cast<const __half2*>(&a01);
+        const __half2* h10 = reinterpret_cast<const __half2*>(&a10); const __half2* h11 = reinterpret_cast<const __half2*>(&a11);
+        const __half2* hs = reinterpret_cast<const __half2*>(&sk);
+        uint4 o, orl;
+        __half2* ho = reinterpret_cast<__half2*>(&o); __half2* hr = reinterpret_cast<__half2*>(&orl);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 v00 = __half22float2(h00[e]), v01 = __half22float2(h01[e]), v10 = __half22float2(h10[e]), v11 = __half22float2(h11[e]);
+            const float2 s2 = __half22float2(hs[e]);
+            const float rx = w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x + s2.x;
+            const float ry = w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y + s2.y;
+            ho[e] = __floats2half2_rn(rx, ry);
+            hr[e] = __floats2half2_rn(fmaxf(rx, 0.f), fmaxf(ry, 0.f));
+        }
+        reinterpret_cast<uint4*>(out)[i] = o;
+        if (out_relu) reinterpret_cast<uint4*>(out_relu)[i] = orl;
     }
 }
 
 // ---------------------------------------------------------------- area down-sampling by f (+ optional extra channel)
-// out[b][y][x][c] = mean over fxf of in; channel C (if extra) = mean of extra[b][.][.]; channels up to cpad are zero
+// out[b][y][x][c] = mean over fxf of in; channel C (if extra) = mean of extra[b][.][.]; channels up to cpad are zero.
+// 8 output channels per thread (C and cpad multiples of 8).
 __global__ void area_down_kernel(const __half* __restrict__ in, const __half* __restrict__ extra, int B, int H, int W, int C,
                                  int f, int cpad, __half* __restrict__ out) {
     pdl_wait();
     pdl_launch_dependents();
-    const int Ho = H / f, Wo = W / f;
-    const size_t total = (size_t)B * Ho * Wo * cpad;
+    const int Ho = H / f, Wo = W / f, P8 = cpad / 8;
+    const size_t total = (size_t)B * Ho * Wo * P8;
     const float inv = 1.f / (f * f);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = i % cpad;
-        size_t p = i / cpad;
+        const int c8 = i % P8;
+        size_t p = i / P8;
         const int xo = p % Wo; p /= Wo;
         const int yo = p % Ho;
         const int b = p / Ho;
-        float s = 0.f;
-        if (c < C) {
+        float s[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] = 0.f;
+        if (c8 * 8 < C) {
             for (int dy = 0; dy < f; ++dy)
-                for (int dx = 0; dx < f; ++dx)
-                    s += __half2float(in[(((size_t)b * H + yo * f + dy) * W + xo * f + dx) * C + c]);
-            s *= inv;
-        } else if (c == C && extra) {
+                for (int dx = 0; dx < f; ++dx) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * H + yo * f + dy) * W + xo * f + dx) * C + c8 * 8));
+                    const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { const float2 v = __half22float2(hh[e]); s[2 * e] += v.x; s[2 * e + 1] += v.y; }
+                }
+        } else if (c8 * 8 == C && extra) {
             for (int dy = 0; dy < f; ++dy)
-                for (int dx = 0; dx < f; ++dx)
-                    s += __half2float(extra[((size_t)b * H + yo * f + dy) * W + xo * f + dx]);
-            s *= inv;
+                for (int dx = 0; dx < f; ++dx) s[0] += __half2float(extra[((size_t)b * H + yo * f + dy) * W + xo * f + dx]);
         }
-        out[i] = __float2half_rn(s);
+        uint4 o;
+        __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ho[e] = __floats2half2_rn(s[2 * e] * inv, s[2 * e + 1] * inv);
+        reinterpret_cast<uint4*>(out)[i] = o;
+    }
+}
+
+// ---------------------------------------------------------------- single-output 3x3 convolution (decoder.pred, modules.py:227,239)
+// logits[b][y][x] = bias + sum_{tap,c} w[tap][c] * in[b][y+dy][x+dx][c].  One warp per output pixel, lanes split channels.
+__global__ void conv3x3_c1_kernel(const __half* __restrict__ in, const __half* __restrict__ wgt, float bias, int B, int H, int W, int C,
+                                  __half* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
+    extern __shared__ __half wsm[];                  // [9][C]
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) wsm[i] = wgt[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t npix = (size_t)B * H * W;
+    const int C8 = C / 8;
+    for (size_t pix = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += (size_t)gridDim.x * (blockDim.x >> 5)) {
+        const int x = pix % W, y = (pix / W) % H, b = pix / ((size_t)H * W);
+        float acc = 0.f;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const uint4* src = reinterpret_cast<const uint4*>(in + (((size_t)b * H + yy) * W + xx) * C);
+            const uint4* wv = reinterpret_cast<const uint4*>(wsm + tap * C);
+            for (int c8 = lane; c8 < C8; c8 += 32) {
+                const uint4 a = __ldg(src + c8), ww = wv[c8];
+                const __half2* ha = reinterpret_cast<const __half2*>(&a); const __half2* hw2 = reinterpret_cast<const __half2*>(&ww);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 fa = __half22float2(ha[e]), fw = __half22float2(hw2[e]);
+                    acc += fa.x * fw.x + fa.y * fw.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[pix] = __float2half_rn(acc + bias);
     }
 }
 
@@ -463,8 +517,8 @@ extern "C" int xm_cbam(const void* x, int32_t B, int32_t H, int32_t W, int32_t C
 
 extern "C" int xm_upsample2x_add(const void* g, const void* skip, int32_t B, int32_t h, int32_t w, int32_t C, void* out, void* out_relu,
                                  void* stream) {
-    XM_REQUIRE(g && skip && out && C % 2 == 0, "xm_upsample2x_add: bad arguments");
-    const size_t total = (size_t)B * 4 * h * w * (C / 2);
+    XM_REQUIRE(g && skip && out && C % 8 == 0, "xm_upsample2x_add: C must be a multiple of 8");
+    const size_t total = (size_t)B * 4 * h * w * (C / 8);
     XM_CHECK_CUDA(tc5_launch(upsample2x_add_kernel, dim3(grid_for(total)), dim3(256), 0, STREAM, (const __half*)g, (const __half*)skip, B, h, w, C, (__half*)out,
                                                                (__half*)out_relu));
     xm_count_launches(1);
@@ -474,11 +528,25 @@ extern "C" int xm_upsample2x_add(const void* g, const void* skip, int32_t B, int
 
 extern "C" int xm_area_down(const void* in, const void* extra, int32_t B, int32_t H, int32_t W, int32_t C, int32_t f, int32_t cpad,
                             void* out, void* stream) {
-    XM_REQUIRE(in && out && f >= 1 && H % f == 0 && W % f == 0 && cpad >= C + (extra ? 1 : 0), "xm_area_down: bad arguments");
-    const size_t total = (size_t)B * (H / f) * (W / f) * cpad;
+    XM_REQUIRE(in && out && f >= 1 && H % f == 0 && W % f == 0 && cpad >= C + (extra ? 1 : 0) && C % 8 == 0 && cpad % 8 == 0,
+               "xm_area_down: bad arguments");
+    const size_t total = (size_t)B * (H / f) * (W / f) * (cpad / 8);
     XM_CHECK_CUDA(tc5_launch(area_down_kernel, dim3(grid_for(total)), dim3(256), 0, STREAM, (const __half*)in, (const __half*)extra, B, H, W, C, f, cpad, (__half*)out));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
+    return XM_OK;
+}
+
+extern "C" int xm_conv3x3_c1(const void* in, const void* weight_tap_c, float bias, int32_t B, int32_t H, int32_t W, int32_t C, void* out,
+                             void* stream) {
+    XM_REQUIRE(in && weight_tap_c && out && C % 8 == 0 && C <= 1024, "xm_conv3x3_c1: bad arguments");
+    const size_t npix = (size_t)B * H * W;
+    int blocks = (int)((npix + 7) / 8);
+    const int cap = xm_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    XM_CHECK_CUDA(tc5_launch(conv3x3_c1_kernel, dim3(blocks), dim3(256), (size_t)9 * C * 2, STREAM, (const __half*)in, (const __half*)weight_tap_c,
+                             bias, B, H, W, C, (__half*)out));
+    xm_count_launches(1);
     return XM_OK;
 }
 

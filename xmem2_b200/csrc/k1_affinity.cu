@@ -329,7 +329,12 @@ k1_scan(const __grid_constant__ K1Maps maps, const K1Seg* __restrict__ sgp, cons
 }
 
 // k-th largest over the per-slice 32-entry lists: one warp per query, lane l owns list l (nlists <= 32).
-// want_den: also 1 / sum_topk exp(S)  (do_softmax top-k branch, memory_util.py:48-49: no max subtraction)
+// Exact selection by bisection on the order-preserving integer image of fp32 (32 branch-free count rounds) instead
+// of k rounds of max extraction.  want_den: also 1 / sum_topk exp(S) (do_softmax top-k branch, memory_util.py:48-49:
+// no max subtraction); entries tied with the k-th value all count, consistently with pass 2's (S >= tau).
+__device__ __forceinline__ uint32_t f2ord(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
+
 __global__ void k1_topk_merge(const float* __restrict__ cand, int nlists, int hw, int hw_pad, int top_k, int want_den,
                               float* __restrict__ tau, float* __restrict__ inv_den) {
     pdl_wait();
@@ -341,43 +346,39 @@ __global__ void k1_topk_merge(const float* __restrict__ cand, int nlists, int hw
         if (lane == 0) { tau[q] = INFINITY; if (want_den) inv_den[q] = 0.f; }
         return;
     }
-    float v[LISTK];
+    uint32_t v[LISTK];
 #pragma unroll
-    for (int u = 0; u < LISTK; ++u) v[u] = -INFINITY;
+    for (int u = 0; u < LISTK; ++u) v[u] = f2ord(-INFINITY);
     if (lane < nlists) {
         const float4* src = reinterpret_cast<const float4*>(cand + ((size_t)lane * hw_pad + q) * LISTK);
 #pragma unroll
         for (int u = 0; u < LISTK / 4; ++u) {
-            float4 f = src[u];
-            v[4 * u] = f.x; v[4 * u + 1] = f.y; v[4 * u + 2] = f.z; v[4 * u + 3] = f.w;
+            const float4 f = src[u];
+            v[4 * u] = f2ord(f.x); v[4 * u + 1] = f2ord(f.y); v[4 * u + 2] = f2ord(f.z); v[4 * u + 3] = f2ord(f.w);
         }
     }
-    float den = 0.f, kth = -INFINITY;
-    for (int r = 0; r < top_k; ++r) {
-        float t16[16], t8[8], t4[4];
+    // largest t with count(v >= t) >= top_k  ==  the top_k-th largest value (if fewer finite entries: -inf's image)
+    uint32_t t = 0u;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t trial = t | (1u << bit);
+        int c = 0;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) t16[u] = fmaxf(v[u], v[u + 16]);
+        for (int u = 0; u < LISTK; ++u) c += (v[u] >= trial) ? 1 : 0;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) t8[u] = fmaxf(t16[u], t16[u + 8]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) t4[u] = fmaxf(t8[u], t8[u + 4]);
-        const float m = fmaxf(fmaxf(t4[0], t4[2]), fmaxf(t4[1], t4[3]));
-        float g = m;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, o));
-        const unsigned owners = __ballot_sync(0xffffffffu, m == g);
-        if (lane == __ffs(owners) - 1) {         // remove ONE instance of the maximum from its owner
-            unsigned eq = 0u;
-#pragma unroll
-            for (int u = 0; u < LISTK; ++u) eq |= (v[u] == g ? 1u : 0u) << u;
-            const int first = __ffs(eq) - 1;
-#pragma unroll
-            for (int u = 0; u < LISTK; ++u) v[u] = (u == first) ? -INFINITY : v[u];
-        }
-        den += fast_exp(g);
-        kth = g;
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (c >= top_k) t = trial;
     }
-    if (lane == 0) { tau[q] = kth; if (want_den) inv_den[q] = 1.f / den; }
+    const float kth = ord2f(t);
+    if (want_den) {
+        float den = 0.f;
+#pragma unroll
+        for (int u = 0; u < LISTK; ++u) den += (v[u] >= t) ? fast_exp(ord2f(v[u])) : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+        if (lane == 0) inv_den[q] = 1.f / den;
+    }
+    if (lane == 0) tau[q] = kth;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -41,9 +41,9 @@ class InferenceCore:
         # steady-state frames (no mask, not a memory frame) are replayed from a CUDA graph: ~90 kernel launches per
         # frame would otherwise be bound by host launch latency, not by the GPU.  `use_cuda_graph=False` disables it.
         self.use_cuda_graph = config.get('use_cuda_graph', True)
-        self._graph = None
-        self._graph_sig = None
-        self._graph_warm_sig = None
+        self._graphs = {}
+        self._graph_warm = set()
+        self._g_out = None
         # warm-up on the network's own device (the reference hard-codes cuda:0, inference_core.py:26)
         dev = next(network.parameters()).device
         if dev.type == 'cuda':
@@ -55,8 +55,7 @@ class InferenceCore:
         if not self.deep_update_sync:
             self.last_deep_update_ti = -self.deep_update_every
         self.memory = self.memory.copy_perm_mem_only() if keep_permanent else MemoryManager(config=self.config)
-        self._graph = None
-        self._graph_sig = None
+        self._graphs = {}
 
     def update_config(self, config):
         self.mem_every = config['mem_every']
@@ -97,12 +96,22 @@ class InferenceCore:
         is_mem_frame, is_deep_update, is_normal_update = self._schedule(mask is not None, end, manually_curated_masks)
         need_segment = (valid_labels is None) or (len(self.all_labels) != len(valid_labels))
 
-        if (self.use_cuda_graph and mask is None and need_segment and is_normal_update and not is_mem_frame and not end
-                and not disable_memory_updates and not return_key_and_stuff and image.is_cuda
-                and self.memory.get_hidden() is not None):
-            prob = self._graph_step(image)
-            if prob is not None:
-                return unpad(prob, self.pad)
+        if (self.use_cuda_graph and mask is None and need_segment and not end and not disable_memory_updates
+                and not return_key_and_stuff and image.is_cuda and self.memory.get_hidden() is not None):
+            if is_normal_update and not is_mem_frame:
+                prob = self._graph_step(image, mem_frame=False)
+                if prob is not None:
+                    return unpad(prob, self.pad)
+            elif is_mem_frame and is_deep_update and self.deep_update_sync and not do_not_add_mask_to_memory:
+                prob = self._graph_step(image, mem_frame=True)
+                if prob is not None:
+                    # the recorded graph produced key/shrinkage/value/selection and the deep-updated hidden state;
+                    # the arena append has a moving offset and stays eager (inference_core.py:136-145)
+                    self.memory.add_memory(self._g_out['key'], self._g_out['shrinkage'], self._g_out['value'], self.all_labels,
+                                           selection=self._g_out['selection'] if self.enable_long_term else None, ignore=False)
+                    self.last_mem_ti = self.curr_ti
+                    self.last_deep_update_ti = self.curr_ti
+                    return unpad(prob, self.pad)
 
         key, shrinkage, selection, f16, f8, f4 = self.network.encode_key(
             image, need_ek=(self.enable_long_term or need_segment), need_sk=True)
@@ -150,74 +159,86 @@ class InferenceCore:
         return res
 
     # ------------------------------------------------------------------ CUDA-graph replay of steady-state frames
-    def _graph_step(self, image):
-        """encode_key -> match_memory -> segment(h_out=True) -> hidden update for one ordinary frame, replayed from a
-        recorded CUDA graph.  The graph depends on the image shape and on the memory arenas' addresses/capacities and
-        group structure (MemoryManager.layout_signature); bank SIZES live in a device-side plan that is refreshed
-        (stream ordered) whenever a memory frame changed them.  Returns None when this frame must run eagerly
-        (first frame with a new signature = warm-up of lazily initialised kernel state)."""
+    def _graph_step(self, image, mem_frame):
+        """One frame replayed from a recorded CUDA graph.
+          mem_frame=False: encode_key -> match_memory -> segment(h_out=True) -> hidden update        (ordinary frame)
+          mem_frame=True : encode_key -> match_memory -> segment(h_out=False) -> encode_value(deep)  (memory frame)
+        The graph depends on the image shape and on the memory arenas' addresses/capacities and group structure
+        (MemoryManager.layout_signature); bank SIZES live in a device-side plan that is refreshed (stream ordered)
+        whenever a memory frame changed them.  Returns None when this frame must run eagerly (first frame with a new
+        signature = warm-up of lazily initialised kernel state)."""
         mem = self.memory
-        sig = (tuple(image.shape), mem.layout_signature(), len(self.all_labels))
-        if self._graph is None or self._graph_sig != sig:
-            cached = _GRAPH_CACHE.get((id(self.network), sig))
-            if cached is not None:
-                self._graph, self._g_image, self._g_hidden, self._g_prob, self._graph_launches, self._g_owner = cached
-                self._graph_sig = sig
-            else:
-                if self._graph_warm_sig != sig:
-                    self._graph_warm_sig = sig          # run this frame eagerly, record on the next one
-                    self._graph = None
+        sig = (tuple(image.shape), mem.layout_signature(), len(self.all_labels), bool(mem_frame))
+        g = self._graphs.get(sig)
+        if g is None:
+            g = _GRAPH_CACHE.get((id(self.network), sig))
+            if g is None:
+                if sig not in self._graph_warm:
+                    self._graph_warm.add(sig)           # run this frame eagerly, record on the next one
                     return None
-                self._capture(image, sig)
+                g = self._capture(image, mem_frame)
                 if len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
                     _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
-                self._g_owner = [None]
-                _GRAPH_CACHE[(id(self.network), sig)] = (self._graph, self._g_image, self._g_hidden, self._g_prob,
-                                                         self._graph_launches, self._g_owner)
+                _GRAPH_CACHE[(id(self.network), sig)] = g
+            self._graphs = {sig: g, **{k: v for k, v in self._graphs.items() if k[:3] == sig[:3]}}
         # the graph's hidden-state buffer is shared by every core using this graph: hand the previous user its own copy
-        prev = self._g_owner[0]() if self._g_owner[0] is not None else None
+        g_hidden = g['hidden']
+        prev = g['owner'][0]() if g['owner'][0] is not None else None
         if prev is not None and prev is not self:
             ph = prev.memory.get_hidden()
-            if ph is not None and ph.data_ptr() == self._g_hidden.data_ptr():
+            if ph is not None and ph.data_ptr() == g_hidden.data_ptr():
                 prev.memory.set_hidden(ph.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3))
-        self._g_owner[0] = weakref.ref(self)
+        g['owner'][0] = weakref.ref(self)
         hid = mem.get_hidden()
-        if hid.data_ptr() != self._g_hidden.data_ptr():
-            self._g_hidden.copy_(hid)
-            mem.set_hidden(self._g_hidden)
-        self._g_image.copy_(image)
+        if hid.data_ptr() != g_hidden.data_ptr():
+            g_hidden.copy_(hid)
+            mem.set_hidden(g_hidden)
+        g['image'].copy_(image)
         h, w = image.shape[-2] // 16, image.shape[-1] // 16
         mem.upload_plan(h * w, image.device)
-        self._graph.replay()
-        lib.load().xm_add_launch_count(self._graph_launches)
-        return self._g_prob
+        g['graph'].replay()
+        lib.load().xm_add_launch_count(g['launches'])
+        self._g_out = g
+        return g['prob']
 
-    def _capture(self, image, sig):
+    def _capture(self, image, mem_frame):
         t0 = time.perf_counter()
         mem, net = self.memory, self.network
         dev = image.device
         n = len(self.all_labels)
         h, w = image.shape[-2] // 16, image.shape[-1] // 16
-        self._g_image = image.clone()
-        self._g_hidden = torch.zeros((1, n, h, w, mem.hidden_dim), device=dev).permute(0, 1, 4, 2, 3)
-        self._g_hidden.copy_(mem.get_hidden())
-        mem.set_hidden(self._g_hidden)
+        g = {'image': image.clone()}
+        # all graphs of one memory layout share ONE hidden-state buffer (ordinary and memory frames alternate) and
+        # therefore one owner record
+        src = next(iter(self._graphs.values()), None)
+        if src is not None and src['hidden'].shape[1] == n:
+            shared, g['owner'] = src['hidden'], src['owner']
+        else:
+            shared, g['owner'] = torch.zeros((1, n, h, w, mem.hidden_dim), device=dev).permute(0, 1, 4, 2, 3), [None]
+        g['hidden'] = shared
+        if mem.get_hidden().data_ptr() != shared.data_ptr():
+            shared.copy_(mem.get_hidden())
+            mem.set_hidden(shared)
         mem.upload_plan(h * w, dev)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         launches0 = lib.load().xm_launch_count()
         with torch.cuda.graph(graph):
-            key, _, selection, f16, f8, f4 = net.encode_key(self._g_image, need_ek=True, need_sk=True)
+            key, shrinkage, selection, f16, f8, f4 = net.encode_key(g['image'], need_ek=True, need_sk=True)
             readout = mem.match_memory(key, selection).unsqueeze(0)
-            hidden, _, prob = net.segment((f16, f8, f4), readout, self._g_hidden, h_out=True, strip_bg=False)
-            self._g_hidden.copy_(hidden)
-            self._g_prob = prob[0]
-        self._graph, self._graph_sig = graph, sig
-        self._graph_launches = int(lib.load().xm_launch_count() - launches0)     # recorded, not executed
-        lib.load().xm_add_launch_count(-self._graph_launches)
+            hidden, _, prob = net.segment((f16, f8, f4), readout, shared, h_out=not mem_frame, strip_bg=False)
+            g['prob'] = prob[0]
+            if mem_frame:
+                value, hidden = net.encode_value(g['image'], f16, shared, prob[0][1:].unsqueeze(0), is_deep_update=True)
+                g.update(key=key, shrinkage=shrinkage, selection=selection, value=value)
+            shared.copy_(hidden)
+        g['graph'] = graph
+        g['launches'] = int(lib.load().xm_launch_count() - launches0)     # recorded, not executed
+        lib.load().xm_add_launch_count(-g['launches'])
         if os.environ.get('XMEM_TRACE'):
             torch.cuda.synchronize(dev)
-            print(f'[xmem2_b200] recorded frame graph in {time.perf_counter() - t0:.3f}s', flush=True)
+            print(f'[xmem2_b200] recorded {"memory" if mem_frame else "ordinary"}-frame graph in {time.perf_counter() - t0:.3f}s', flush=True)
+        return g
 
     def put_to_permanent_memory(self, image, mask, ti=None):
         """encode an annotated frame straight into permanent memory (inference_core.py:154-179)."""

@@ -91,6 +91,7 @@ def load() -> C.CDLL:
         lib.xm_upsample2x_add.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp]
         lib.xm_area_down.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
         lib.xm_gru.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+        lib.xm_conv3x3_c1.argtypes = [vp, vp, f32, i32, i32, i32, i32, vp, vp]
         lib.xm_upsample4x_aggregate.argtypes = [vp, i32, i32, i32, vp, vp, vp]
         lib.xm_value_append.argtypes = [vp, i32, i32, vp, i64, i32, vp]
         _lib = lib

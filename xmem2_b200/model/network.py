@@ -163,6 +163,8 @@ class XMem(nn.Module):
                 'ChannelGate.mlp.1.weight', 'ChannelGate.mlp.1.bias', 'ChannelGate.mlp.3.weight', 'ChannelGate.mlp.3.bias')) + (
                 self._w(a + 'SpatialGate.spatial.conv.weight').reshape(-1).contiguous().to(device),
                 float(self._w(a + 'SpatialGate.spatial.conv.bias').item()))
+        wpred, bpred = self._folded('decoder.pred')
+        pk['decoder.pred.direct'] = (wpred[0].permute(1, 2, 0).reshape(9, -1).half().contiguous().to(device), float(bpred.item()))
         self._pk, self._pk_device = pk, device
         self._sd = None
 
@@ -213,14 +215,15 @@ class XMem(nn.Module):
         h16 = torch.empty(h32.shape, dtype=torch.float16, device=h32.device)
         lib.check(lib.load().xm_gru(values.data_ptr(), h32.data_ptr(), npix, self.hidden_dim, h_new.data_ptr(), h16.data_ptr(),
                                     lib.stream_ptr()), 'xm_gru')
-        self._h16_cache = (h_new.data_ptr(), h16)
+        self._h16_cache = (h_new, h16)       # holding h_new keeps its storage from being recycled under the cached pointer
         return h_new
 
     def _hidden_pair(self, hidden5):
         """hidden [1,n,64,h,w] fp32 (any layout) -> (h32 NHWC [n,h,w,64] fp32 contiguous, h16 same fp16)."""
         h32 = _as_nhwc(hidden5[0], torch.float32)
-        if self._h16_cache is not None and self._h16_cache[0] == h32.data_ptr():
-            return h32, self._h16_cache[1]
+        c = self._h16_cache
+        if c is not None and c[0].data_ptr() == h32.data_ptr() and c[0].shape == h32.shape:
+            return h32, c[1]
         return h32, h32.half()
 
     # ------------------------------------------------------------------ public passes
@@ -321,7 +324,10 @@ class XMem(nn.Module):
 
         g8 = up_block(f8, g16, 'decoder.up_16_8', False)
         g4, g4r = up_block(f4, g8, 'decoder.up_8_4', True)
-        logits4 = self._conv('decoder.pred', [(g4r, False)])                # [n,4h,4w,1]
+        wpd, bpd = self._pk['decoder.pred.direct']
+        logits4 = torch.empty((n, 4 * h, 4 * w, 1), dtype=torch.float16, device=dev)
+        lib.check(L.xm_conv3x3_c1(g4r.data_ptr(), wpd.data_ptr(), C.c_float(bpd), n, 4 * h, 4 * w, g4r.shape[3], logits4.data_ptr(),
+                                  lib.stream_ptr()), 'xm_conv3x3_c1')
         new_hidden = None
         if h_out and self.hidden_dim > 0:
             a = self._conv('decoder.hidden_update.g16_conv', [(g16, False)])
