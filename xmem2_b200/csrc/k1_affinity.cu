@@ -398,7 +398,9 @@ struct P2Smem {
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(SCAN_THREADS, 1)
+constexpr int P2_THREADS = 64 + 512;     // warp 0 TMA, warp 1 MMA, 16 softmax warps: 4 per TMEM lane quadrant, 16 columns each
+
+__global__ void __launch_bounds__(P2_THREADS, 1)
 k1_readout_pass2(const __grid_constant__ K1Maps maps, const K1Seg* __restrict__ sgp, const float* __restrict__ bsq,
                  const float* __restrict__ tau, const float* __restrict__ inv_den, int hw_pad, int obj_begin,
                  int n_obj, int do_usage, float* __restrict__ partial) {
@@ -423,8 +425,8 @@ k1_readout_pass2(const __grid_constant__ K1Maps maps, const K1Seg* __restrict__ 
         mbar_init(&sm.qfull, 1);
         for (int i = 0; i < P2_KSTAGES; ++i) { mbar_init(&sm.kfull[i], 1); mbar_init(&sm.kempty[i], 1); }
         for (int i = 0; i < P2_VSTAGES; ++i) { mbar_init(&sm.vfull[i], 1); mbar_init(&sm.vempty[i], 1); }
-        for (int i = 0; i < P2_SBUF; ++i) { mbar_init(&sm.sfull[i], 1); mbar_init(&sm.sempty[i], 256); }
-        for (int i = 0; i < P2_PBUF; ++i) { mbar_init(&sm.pfull[i], 256); mbar_init(&sm.pempty[i], 1); }
+        for (int i = 0; i < P2_SBUF; ++i) { mbar_init(&sm.sfull[i], 1); mbar_init(&sm.sempty[i], 512); }
+        for (int i = 0; i < P2_PBUF; ++i) { mbar_init(&sm.pfull[i], 512); mbar_init(&sm.pempty[i], 1); }
         mbar_init(&sm.ofull, 1);
         fence_mbar_init();
     }
@@ -506,92 +508,120 @@ k1_readout_pass2(const __grid_constant__ K1Maps maps, const K1Seg* __restrict__ 
         }
     } else {
         const int lane_base = (warp & 3) * 32;
-        const int half = (warp - 2) >> 2;
+        const int quarter = (warp - 2) >> 2;           // which 16 of the tile's 64 columns
         const int row = lane_base + lane;
         const int q = qtile * TQ + row;
         const float bsq8 = bsq[q] * 0.125f;
         const float my_tau = tau[q];
         const float my_inv = inv_den[q];
         const bool usage_cta = do_usage && blockIdx.y == 0;
-        float ms_next[32];
-        auto load_ms = [&](int i, float (&ms)[32]) {
+        // The affinity tile is ~99.9 % zeros (k of N columns per query).  The two P buffers are zeroed once; per tile a
+        // thread only evaluates the threshold test, writes its few non-zero entries and remembers them (bit mask per
+        // buffer) so that it can clear them again when the buffer comes round.
+        {
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int pb = 0; pb < P2_PBUF; ++pb)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) *reinterpret_cast<uint4*>(sm.p[pb] + row * 128 + (((quarter * 2 + c) ^ (row & 7)) << 4)) = z;
+            fence_proxy_async_smem();
+        }
+        uint32_t written0 = 0u, written1 = 0u;
+        auto p_addr = [&](int pb, int j) -> __half* {          // element (row, column quarter*16 + j) of the swizzled P tile
+            const int n = quarter * 16 + j;
+            return reinterpret_cast<__half*>(sm.p[pb] + row * 128 + (((n >> 3) ^ (row & 7)) << 4) + (n & 7) * 2);
+        };
+        auto load_ms = [&](int i, float (&ms)[16]) {
             int s, col, lo, nv;
             locate_tile(sg, t_begin + i, s, col, lo, nv);
-            const int c0 = col + half * 32;
-            const int jlo = lo - half * 32, jhi = nv - half * 32;
+            const int c0 = col + quarter * 16;
+            const int jlo = lo - quarter * 16, jhi = nv - quarter * 16;
             const float* shr = sg.shr[s] + c0;
-            if (jlo <= 0 && jhi >= 32) {
+            if (jlo <= 0 && jhi >= 16) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
+                for (int j = 0; j < 16; j += 4) {
                     const float4 f = __ldg(reinterpret_cast<const float4*>(shr + j));
                     ms[j] = f.x; ms[j + 1] = f.y; ms[j + 2] = f.z; ms[j + 3] = f.w;
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) ms[j] = (j >= jlo && j < jhi) ? __ldg(shr + j) : 1.f;
+                for (int j = 0; j < 16; ++j) ms[j] = (j >= jlo && j < jhi) ? __ldg(shr + j) : 1.f;
             }
         };
-        if (nt > 0) load_ms(0, ms_next);
-        for (int i = 0; i < nt; ++i) {
+        auto process = [&](int i, const float (&ms)[16]) {
             int s, col, lo, nv;
             locate_tile(sg, t_begin + i, s, col, lo, nv);
-            float ms[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) ms[j] = ms_next[j];
-            if (i + 1 < nt) load_ms(i + 1, ms_next);
             const int sb = i % P2_SBUF, sph = (i / P2_SBUF) & 1;
             const int pb = i % P2_PBUF, pph = (i / P2_PBUF) & 1;
             mbar_wait(&sm.sfull[sb], sph, 5);
             tc_fence_after();
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_s + (static_cast<uint32_t>(lane_base) << 16) + sb * TN + half * 32, r);
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tmem_s + (static_cast<uint32_t>(lane_base) << 16) + sb * TN + quarter * 16, r);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&sm.sempty[sb]);
-            const int c0 = col + half * 32;
-            const int jlo = lo - half * 32, jhi = nv - half * 32;
-            const bool full_tile = (jlo <= 0) && (jhi >= 32);
+            const int c0 = col + quarter * 16;
+            const int jlo = lo - quarter * 16, jhi = nv - quarter * 16;
+            const bool full_tile = (jlo <= 0) && (jhi >= 16);
             float* usage = (usage_cta && sg.usage[s]) ? sg.usage[s] + c0 : nullptr;
-            // branch-free: p = (S >= tau) ? exp(S) / den : 0   (k of N columns are non-zero)
-            float pv[32];
+            uint32_t h0 = 0u, h1 = 0u, h2 = 0u, h3 = 0u;          // four independent accumulation chains (ILP)
+            if (full_tile) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float sc = score2(r[j], bsq8, ms[j]);
-                const bool ok = (sc >= my_tau) && (full_tile || (j >= jlo && j < jhi));
-                pv[j] = ok ? fast_exp(sc) * my_inv : 0.f;
+                for (int j = 0; j < 4; ++j) {
+                    h0 |= (score2(r[j], bsq8, ms[j]) >= my_tau) ? (1u << j) : 0u;
+                    h1 |= (score2(r[4 + j], bsq8, ms[4 + j]) >= my_tau) ? (16u << j) : 0u;
+                    h2 |= (score2(r[8 + j], bsq8, ms[8 + j]) >= my_tau) ? (256u << j) : 0u;
+                    h3 |= (score2(r[12 + j], bsq8, ms[12 + j]) >= my_tau) ? (4096u << j) : 0u;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) h0 |= ((j >= jlo && j < jhi) && score2(r[j], bsq8, ms[j]) >= my_tau) ? (1u << j) : 0u;
             }
-            if (usage) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (pv[j] > 0.f) atomicAdd(usage + j, pv[j]);
-            }
-            uint32_t packed[16];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) packed[j >> 1] = pack_half2(pv[j], pv[j + 1]);
+            const uint32_t hit = h0 | h1 | h2 | h3;              // bit j: S[q, c0 + j] >= tau  (k of N columns)
             mbar_wait(&sm.pempty[pb], pph ^ 1, 9);
-            uint8_t* prow = sm.p[pb] + row * 128;
+            const uint32_t old = pb ? written1 : written0;
+            if (old | hit) {                                      // rare: this thread owns non-zero affinity entries
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int chunk = half * 4 + c;
-                uint4 val = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
-                *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = val;
+                for (int j = 0; j < 16; ++j) {
+                    if ((old >> j) & 1u) *p_addr(pb, j) = __float2half(0.f);
+                    if ((hit >> j) & 1u) {
+                        const float pv = fast_exp(score2(r[j], bsq8, ms[j])) * my_inv;
+                        *p_addr(pb, j) = __float2half_rn(pv);
+                        if (usage) atomicAdd(usage + j, pv);
+                    }
+                }
             }
+            if (pb) written1 = hit; else written0 = hit;
             fence_proxy_async_smem();
             mbar_arrive(&sm.pfull[pb]);
+        };
+        static_assert(P2_PBUF == 2, "the non-zero bookkeeping assumes two P buffers");
+        // two tiles per iteration with ping-pong shrinkage registers: the loads for tile i+1 are in flight while
+        // tile i is processed (no register copies)
+        float msA[16], msB[16];
+        if (nt > 0) load_ms(0, msA);
+        for (int i = 0; i < nt; i += 2) {
+            if (i + 1 < nt) load_ms(i + 1, msB);
+            process(i, msA);
+            if (i + 1 < nt) {
+                if (i + 2 < nt) load_ms(i + 2, msA);
+                process(i + 1, msB);
+            }
         }
-        // epilogue: warp pair member `half` drains O^T chunk m = half (lane = channel, columns = queries)
+        // epilogue: the 4 warps of a lane quadrant drain O^T chunk m = quarter>>1, query columns (quarter&1)*64..+63
         mbar_wait(&sm.ofull, 0, 10);
         tc_fence_after();
         const int n_obj_all = gridDim.y >> 1;
         (void)n_obj;
         {
-            const int m = half;
+            const int m = quarter >> 1, qh = quarter & 1;
             const int c = chalf * CHALF + m * 128 + row;
-            float* dst = partial + (((size_t)split * n_obj_all + obj) * XM_CV + c) * hw_pad + qtile * TQ;
+            float* dst = partial + (((size_t)split * n_obj_all + obj) * XM_CV + c) * hw_pad + qtile * TQ + qh * 64;
 #pragma unroll 1
-            for (int qq = 0; qq < 4; ++qq) {
+            for (int qq = 0; qq < 2; ++qq) {
                 uint32_t r[32];
                 if (nt > 0) {
-                    tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(lane_base) << 16) + m * 128 + qq * 32, r);
+                    tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(lane_base) << 16) + m * 128 + qh * 64 + qq * 32, r);
                     tmem_ld_wait();
                 } else {
 #pragma unroll
@@ -806,7 +836,7 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
         int nsplit2 = sms / ctas_per_slice;               // one wave
         nsplit2 = nsplit2 < 1 ? 1 : nsplit2;
         if (nsplit2 > K1_MAX_SPLIT) nsplit2 = K1_MAX_SPLIT;
-        XM_CHECK_CUDA(tc5_launch(k1_readout_pass2, dim3(qtiles, 2 * gr.n_obj, nsplit2), dim3(SCAN_THREADS), sizeof(P2Smem) + 1024, stream,
+        XM_CHECK_CUDA(tc5_launch(k1_readout_pass2, dim3(qtiles, 2 * gr.n_obj, nsplit2), dim3(P2_THREADS), sizeof(P2Smem) + 1024, stream,
                                  maps, sgp, a->bsq, (const float*)tau, (const float*)inv_den, hw_pad, gr.obj_begin, gr.n_obj, g == 0 ? 1 : 0, partial));
         XM_CHECK_CUDA(cudaGetLastError());
         xm_count_launches(6);
