@@ -88,6 +88,17 @@ int xm_affinity_readout(const xm_affinity_args_t* args, void* stream);
  * on (hw, n_obj_total, group object counts), never on bank sizes.                                          */
 int xm_affinity_plan(const xm_affinity_args_t* args, void* host_plan_out, int64_t bytes);
 
+/* T-sharded read: the banks of one long video are split over R ranks by stored frame; every rank
+ * has the same query.  The host interleaves the collectives (torch.distributed / NCCL):
+ *   stage_a -> all_reduce(MAX) tau_lo[hw_pad] -> stage_b -> all_gather top32[R][hw_pad][32] -> merge (every rank)
+ *   -> stage_c -> all_reduce(SUM) readout_f32[n_obj][512][hw_pad] -> cast.   One object group per call (groups[0]);
+ * a rank may hold fewer than top_k (even zero) columns.  Same math as xm_affinity_readout (model/memory_util.py:7-65). */
+int xm_affinity_tshard_stage_a(const xm_affinity_args_t* args, float* tau_lo_local, void* stream);
+int xm_affinity_tshard_stage_b(const xm_affinity_args_t* args, const float* tau_lo_global, float* top32_local, void* stream);
+int xm_affinity_tshard_merge(const float* top32_all, int32_t n_ranks, int32_t hw, int32_t hw_pad, int32_t top_k, float* tau, float* inv_den, void* stream);
+int xm_affinity_tshard_stage_c(const xm_affinity_args_t* args, const float* tau, const float* inv_den, float* readout_f32, void* stream);
+int xm_affinity_tshard_cast(const float* readout_f32, int32_t n_obj, int32_t hw, int32_t hw_pad, void* readout_chw, void* readout_hwc, void* stream);
+
 /* key [hw][64] fp16 (NHWC), selection [hw][64] fp16 -> qp [hw_pad][128] = (-e, 2*k*e), bsq = sum_c e*k^2 */
 int xm_query_pack(const void* key_hwc, const void* sel_hwc, int32_t hw, int32_t hw_pad, void* qp, float* bsq, void* stream);
 /* key [n][64] fp16 -> rows [n][128] = (k^2, k) written at dst */

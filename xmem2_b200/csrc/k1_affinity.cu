@@ -381,6 +381,58 @@ __global__ void k1_topk_merge(const float* __restrict__ cand, int nlists, int hw
     if (lane == 0) tau[q] = kth;
 }
 
+// T-sharded mode: compress the per-slice candidate lists of THIS rank to its 32 largest scores per query, the
+// record that is all-gathered across ranks (a rank's 32 largest necessarily contain its share of the global top-k).
+__global__ void k1_export_top32(const float* __restrict__ cand, int nlists, int hw_pad, float* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= hw_pad) return;
+    uint32_t v[LISTK];
+#pragma unroll
+    for (int u = 0; u < LISTK; ++u) v[u] = f2ord(-INFINITY);
+    if (lane < nlists) {
+        const float4* src = reinterpret_cast<const float4*>(cand + ((size_t)lane * hw_pad + q) * LISTK);
+#pragma unroll
+        for (int u = 0; u < LISTK / 4; ++u) {
+            const float4 f = src[u];
+            v[4 * u] = f2ord(f.x); v[4 * u + 1] = f2ord(f.y); v[4 * u + 2] = f2ord(f.z); v[4 * u + 3] = f2ord(f.w);
+        }
+    }
+    uint32_t t = 0u;                                   // image of the 32nd largest local candidate
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t trial = t | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int u = 0; u < LISTK; ++u) c += (v[u] >= trial) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (c >= LISTK) t = trial;
+    }
+    // strictly-greater entries first, then ties with t until the record is full
+    float* dst = out + (size_t)q * LISTK;
+    int mine_gt = 0, mine_eq = 0;
+#pragma unroll
+    for (int u = 0; u < LISTK; ++u) { mine_gt += (v[u] > t) ? 1 : 0; mine_eq += (v[u] == t) ? 1 : 0; }
+    int pre_gt = mine_gt, pre_eq = mine_eq;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, pre_gt, o), b2 = __shfl_up_sync(0xffffffffu, pre_eq, o);
+        if (lane >= o) { pre_gt += a; pre_eq += b2; }
+    }
+    const int total_gt = __shfl_sync(0xffffffffu, pre_gt, 31);
+    int pos_gt = pre_gt - mine_gt, pos_eq = total_gt + pre_eq - mine_eq;
+#pragma unroll
+    for (int u = 0; u < LISTK; ++u) {
+        if (v[u] > t) { dst[pos_gt++] = ord2f(v[u]); }
+        else if (v[u] == t) { if (pos_eq < LISTK) dst[pos_eq] = ord2f(v[u]); ++pos_eq; }
+    }
+    const int filled = min(LISTK, total_gt + __shfl_sync(0xffffffffu, pre_eq, 31));
+    for (int u = filled + lane; u < LISTK; u += 32) dst[u] = -INFINITY;
+}
+
 // ---------------------------------------------------------------------------------------------
 // pass 2: P = (S >= tau) ? exp(S) / den : 0 ;  O^T[c,q] += V[c,n] P[q,n]
 // ---------------------------------------------------------------------------------------------
@@ -664,6 +716,17 @@ __global__ void k1_finish(const float* __restrict__ partial, int nsplit, int n_o
     }
 }
 
+// T-sharded mode: sum the local column slices in fp32 [n_obj][512][hw_pad] (all-reduced across ranks afterwards)
+__global__ void k1_sum_splits(const float* __restrict__ partial, int nsplit, size_t plane, float* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < nsplit; ++s) acc += partial[(size_t)s * plane + i];
+        out[i] = acc;
+    }
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
@@ -709,7 +772,7 @@ static_assert(sizeof(K1Seg) * XM_MAX_GROUPS <= K1_PLAN_BYTES, "plan area too sma
 static_assert(sizeof(K1Seg) % 4 == 0 && sizeof(K1Seg) / 4 <= SCAN_THREADS, "K1Seg is copied by one thread per word");
 
 // Build the per-group column-range tables (host side).  plan_out receives XM_MAX_GROUPS K1Seg records.
-static int k1_build_plan(const xm_affinity_args_t* a, K1Seg* plan) {
+static int k1_build_plan(const xm_affinity_args_t* a, K1Seg* plan, bool allow_small = false) {
     XM_REQUIRE(a->n_groups > 0 && a->n_groups <= XM_MAX_GROUPS, "xm_affinity: bad n_groups %d", a->n_groups);
     for (int g = 0; g < a->n_groups; ++g) {
         const xm_group_t& gr = a->groups[g];
@@ -735,7 +798,8 @@ static int k1_build_plan(const xm_affinity_args_t* a, K1Seg* plan) {
             cols += bk.size - begin;
         }
         for (int s = sg.nseg; s < 4; ++s) sg.tile0[s] = tiles;
-        XM_REQUIRE(cols >= a->top_k, "xm_affinity: group %d sees %d memory columns < top_k=%d (torch.topk would raise)", g, cols, a->top_k);
+        XM_REQUIRE(allow_small || cols >= a->top_k, "xm_affinity: group %d sees %d memory columns < top_k=%d (torch.topk would raise)", g,
+                   cols, a->top_k);
     }
     return XM_OK;
 }
@@ -844,5 +908,132 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
                                  (const float*)partial, nsplit2, gr.n_obj, hw, hw_pad, gr.obj_begin, (__half*)a->readout_chw, (__half*)a->readout_hwc));
         XM_CHECK_CUDA(cudaGetLastError());
     }
+    return XM_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// T-sharded memory read: the banks of ONE long video are distributed over R ranks by stored frame.
+// Every rank holds the same query; the host interleaves three small NCCL collectives between these stages:
+//   stage_a : local slot maxima -> local lower bound                     ... all_reduce(MAX)  tau_lo[hw_pad]
+//   stage_b : local scores > pred(tau_lo) -> local 32 largest per query  ... all_gather       top32[R][hw_pad][32]
+//   merge   : exact global tau, 1/den from the gathered records (every rank, identical result)
+//   stage_c : local P.V with the GLOBAL normalisers -> fp32 partial      ... all_reduce(SUM)  readout_f32
+//   cast    : fp32 -> fp16 CHW / NHWC
+// Single object group per call (groups[0]); usage stays local to the rank that owns the column.
+// ---------------------------------------------------------------------------------------------
+struct TshardCtx {
+    K1Maps maps; K1Seg* plan_dev; float *cand, *tau_lo, *tau, *inv_den, *partial; int qtiles, nsplit1, nsplit2;
+};
+
+static int tshard_setup(const xm_affinity_args_t* a, cudaStream_t stream, TshardCtx& c, bool upload_plan) {
+    XM_REQUIRE(a && a->n_groups == 1, "xm_affinity_tshard: exactly one object group per call");
+    XM_REQUIRE(a->hw > 0 && a->hw_pad == (a->hw + TQ - 1) / TQ * TQ, "xm_affinity_tshard: hw_pad must be hw rounded up to 128");
+    XM_REQUIRE(a->top_k > 0 && a->top_k <= XM_MAX_TOPK && a->qp && a->bsq && a->workspace, "xm_affinity_tshard: bad arguments");
+    XM_REQUIRE(a->workspace_bytes >= xm_affinity_workspace_bytes(a->hw, a->n_obj_total), "xm_affinity_tshard: workspace too small");
+    tc5_debug_init();
+    static bool attr_done = false;
+    if (!attr_done) {
+        XM_CHECK_CUDA(cudaFuncSetAttribute(k1_scan<MODE_SLOTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem) + 1024));
+        XM_CHECK_CUDA(cudaFuncSetAttribute(k1_scan<MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem) + 1024));
+        XM_CHECK_CUDA(cudaFuncSetAttribute(k1_readout_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2Smem) + 1024));
+        attr_done = true;
+    }
+    const int hw_pad = a->hw_pad;
+    uint8_t* ws = (uint8_t*)a->workspace;
+    c.plan_dev = (K1Seg*)ws;        ws += K1_PLAN_BYTES;
+    c.cand = (float*)ws;            ws += align_up((size_t)K1_MAX_SPLIT * hw_pad * LISTK * 4, 256);
+    c.tau_lo = (float*)ws;          ws += align_up((size_t)hw_pad * 4, 256);
+    c.tau = (float*)ws;             ws += align_up((size_t)hw_pad * 4, 256);
+    c.inv_den = (float*)ws;         ws += align_up((size_t)hw_pad * 4, 256);
+    c.partial = (float*)ws;
+    if (upload_plan) {
+        K1Seg plan[XM_MAX_GROUPS];
+        memset(plan, 0, sizeof(plan));
+        const int rc = k1_build_plan(a, plan, /*allow_small=*/true);
+        if (rc != XM_OK) return rc;
+        XM_CHECK_CUDA(cudaMemcpyAsync(c.plan_dev, plan, sizeof(K1Seg), cudaMemcpyHostToDevice, stream));
+    }
+    {
+        uint64_t d[2] = {KP, (uint64_t)hw_pad}; uint64_t st[1] = {KP * 2}; uint32_t b[2] = {64, TQ};
+        if (xm_make_tmap_f16(&c.maps.q, a->qp, 2, d, st, b)) return XM_ERR_CUDA;
+    }
+    for (int i = 0; i < 3; ++i) {
+        const xm_bank_t& bk = a->banks[i];
+        if (!bk.keys || bk.cap <= 0) { c.maps.k[i] = c.maps.q; c.maps.v[i] = c.maps.q; continue; }
+        uint64_t d[2] = {KP, (uint64_t)bk.cap}; uint64_t st[1] = {KP * 2}; uint32_t b[2] = {64, TN};
+        if (xm_make_tmap_f16(&c.maps.k[i], bk.keys, 2, d, st, b)) return XM_ERR_CUDA;
+        uint64_t dv[3] = {(uint64_t)bk.cap, XM_CV, (uint64_t)bk.n_obj_cap};
+        uint64_t sv[2] = {(uint64_t)bk.cap * 2, (uint64_t)bk.cap * 2 * XM_CV};
+        uint32_t bv[3] = {TN, 128, 1};
+        if (xm_make_tmap_f16(&c.maps.v[i], bk.values, 3, dv, sv, bv)) return XM_ERR_CUDA;
+    }
+    const int sms = xm_num_sms();
+    c.qtiles = hw_pad / TQ;
+    c.nsplit1 = sms / c.qtiles; if (c.nsplit1 < 1) c.nsplit1 = 1; if (c.nsplit1 > K1_MAX_SPLIT / 2) c.nsplit1 = K1_MAX_SPLIT / 2;
+    const int per = c.qtiles * 2 * a->groups[0].n_obj;
+    c.nsplit2 = sms / per; if (c.nsplit2 < 1) c.nsplit2 = 1; if (c.nsplit2 > K1_MAX_SPLIT) c.nsplit2 = K1_MAX_SPLIT;
+    return XM_OK;
+}
+
+extern "C" int xm_affinity_tshard_stage_a(const xm_affinity_args_t* a, float* tau_lo_local, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    TshardCtx c;
+    int rc = tshard_setup(a, stream, c, true);
+    if (rc != XM_OK) return rc;
+    XM_REQUIRE(tau_lo_local, "xm_affinity_tshard_stage_a: null output");
+    XM_CHECK_CUDA(tc5_launch(k1_scan<MODE_SLOTMAX>, dim3(c.qtiles, c.nsplit1), dim3(SCAN_THREADS), sizeof(ScanSmem) + 1024, stream,
+                             c.maps, (const K1Seg*)c.plan_dev, a->bsq, (const float*)nullptr, a->hw_pad, c.cand, (float*)nullptr));
+    XM_CHECK_CUDA(tc5_launch(k1_topk_merge, dim3((a->hw_pad + 3) / 4), dim3(128), 0, stream, (const float*)c.cand, c.nsplit1 * 2, a->hw,
+                             a->hw_pad, a->top_k, 0, tau_lo_local, (float*)nullptr));
+    xm_count_launches(2);
+    return XM_OK;
+}
+
+extern "C" int xm_affinity_tshard_stage_b(const xm_affinity_args_t* a, const float* tau_lo_global, float* top32_local, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    TshardCtx c;
+    int rc = tshard_setup(a, stream, c, false);
+    if (rc != XM_OK) return rc;
+    XM_REQUIRE(tau_lo_global && top32_local, "xm_affinity_tshard_stage_b: null pointer");
+    XM_CHECK_CUDA(tc5_launch(k1_scan<MODE_COLLECT>, dim3(c.qtiles, c.nsplit1), dim3(SCAN_THREADS), sizeof(ScanSmem) + 1024, stream,
+                             c.maps, (const K1Seg*)c.plan_dev, a->bsq, tau_lo_global, a->hw_pad, c.cand, (float*)nullptr));
+    XM_CHECK_CUDA(tc5_launch(k1_export_top32, dim3((a->hw_pad + 3) / 4), dim3(128), 0, stream, (const float*)c.cand, c.nsplit1 * 2, a->hw_pad,
+                             top32_local));
+    xm_count_launches(2);
+    return XM_OK;
+}
+
+extern "C" int xm_affinity_tshard_merge(const float* top32_all, int32_t n_ranks, int32_t hw, int32_t hw_pad, int32_t top_k, float* tau,
+                                        float* inv_den, void* stream_) {
+    XM_REQUIRE(top32_all && tau && inv_den && n_ranks >= 1 && n_ranks <= 32, "xm_affinity_tshard_merge: bad arguments (<= 32 ranks)");
+    XM_CHECK_CUDA(tc5_launch(k1_topk_merge, dim3((hw_pad + 3) / 4), dim3(128), 0, (cudaStream_t)stream_, top32_all, n_ranks, hw, hw_pad, top_k, 1,
+                             tau, inv_den));
+    xm_count_launches(1);
+    return XM_OK;
+}
+
+extern "C" int xm_affinity_tshard_stage_c(const xm_affinity_args_t* a, const float* tau, const float* inv_den, float* readout_f32,
+                                          void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    TshardCtx c;
+    int rc = tshard_setup(a, stream, c, false);
+    if (rc != XM_OK) return rc;
+    XM_REQUIRE(tau && inv_den && readout_f32, "xm_affinity_tshard_stage_c: null pointer");
+    const xm_group_t& gr = a->groups[0];
+    XM_CHECK_CUDA(tc5_launch(k1_readout_pass2, dim3(c.qtiles, 2 * gr.n_obj, c.nsplit2), dim3(P2_THREADS), sizeof(P2Smem) + 1024, stream,
+                             c.maps, (const K1Seg*)c.plan_dev, a->bsq, tau, inv_den, a->hw_pad, gr.obj_begin, gr.n_obj, 1, c.partial));
+    const size_t plane = (size_t)gr.n_obj * XM_CV * a->hw_pad;
+    XM_CHECK_CUDA(tc5_launch(k1_sum_splits, dim3(xm_num_sms() * 4), dim3(256), 0, stream, (const float*)c.partial, c.nsplit2, plane, readout_f32));
+    xm_count_launches(2);
+    return XM_OK;
+}
+
+extern "C" int xm_affinity_tshard_cast(const float* readout_f32, int32_t n_obj, int32_t hw, int32_t hw_pad, void* readout_chw,
+                                       void* readout_hwc, void* stream_) {
+    XM_REQUIRE(readout_f32 && (readout_chw || readout_hwc) && n_obj >= 1, "xm_affinity_tshard_cast: bad arguments");
+    XM_CHECK_CUDA(tc5_launch(k1_finish, dim3((hw + 31) / 32, XM_CV / 32, n_obj), dim3(32, 8), 0, (cudaStream_t)stream_, readout_f32, 1, n_obj, hw,
+                             hw_pad, 0, (__half*)readout_chw, (__half*)readout_hwc));
+    xm_count_launches(1);
     return XM_OK;
 }
