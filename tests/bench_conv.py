@@ -54,14 +54,14 @@ for name, B, H, W, cins, cout, k, s, cnt in SHAPES:
     for _ in range(5):
         lib.conv2d_nhwc(srcs, wp, bp, cout, ksize=k, stride=s, relu=True, out=out)
     torch.cuda.synchronize()
-    n = 20 if not only else 3
+    n = 20
     # record n back-to-back launches in a CUDA graph so the host launch path is not what gets timed
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         for _ in range(n):
             lib.conv2d_nhwc(srcs, wp, bp, cout, ksize=k, stride=s, relu=True, out=out)
     graph.replay(); torch.cuda.synchronize()
-    reps = 10 if not only else 1
+    reps = 10
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):

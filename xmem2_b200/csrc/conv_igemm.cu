@@ -17,6 +17,8 @@
 //   Channel-concatenated inputs (torch.cat along C in the reference) are read from up to three source
 //   tensors without materialising the concat; a source may be broadcast over the batch.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
+#include <cstdio>
+#include <cstdlib>
 #include "common.h"
 #include "tc5.cuh"
 
@@ -345,7 +347,21 @@ extern "C" int xm_conv2d_nhwc(const xm_conv_args_t* a, void* stream_) {
             if (xm_make_tmap_f16(&maps.a[s], a->src[ss].ptr, 5, d, st, bx)) return XM_ERR_CUDA;
         }
     }
-    const int BN = (a->cout_pad % 128 == 0) ? 128 : 64;
+    // debug/tuning override: XMEM_CONV_FORCE="bn,splits,stages" (0 = keep the heuristic)
+    static int f_bn = -1, f_split = 0, f_depth = 0;
+    if (f_bn < 0) {
+        f_bn = 0;
+        if (const char* e = getenv("XMEM_CONV_FORCE")) sscanf(e, "%d,%d,%d", &f_bn, &f_split, &f_depth);
+    }
+    // N tile: 128 couts when that already gives at least half a wave of CTAs, else 64 (more CTAs beat split-K: the
+    // split-K fix-up costs ~10 us, measured in profiles/r1_conv_config_sweep.txt)
+    const int sms_ = xm_num_sms();
+    int BN = (a->cout_pad % 128 == 0) ? 128 : 64;
+    int cb_all = 0;
+    for (int s = 0; s < p.n_src; ++s) cb_all += p.cblocks[s];
+    const int ksteps_all = a->ksize * a->ksize * cb_all;
+    if (BN == 128 && ksteps_all <= 128 && p.tiles_x * p.tiles_y * p.batch * (a->cout_pad / 128) * 2 <= sms_) BN = 64;
+    if (f_bn == 64 || (f_bn == 128 && a->cout_pad % 128 == 0)) BN = f_bn;
     {
         const uint64_t K = (uint64_t)a->ksize * a->ksize * p.cin_total;
         uint64_t d[2] = {K, (uint64_t)a->cout_pad};
@@ -361,20 +377,23 @@ extern "C" int xm_conv2d_nhwc(const xm_conv_args_t* a, void* stream_) {
     const int ctas = p.tiles_x * p.tiles_y * p.batch * (a->cout_pad / BN);
     const int sms = xm_num_sms();
     p.splits = 1;
-    if (a->workspace && ctas * 2 <= sms) {
+    if (a->workspace && ((ctas * 3 <= sms && ksteps >= 48) || (ctas * 2 <= sms && ksteps > 128))) {   // small grids, long K loops
         int s = sms / ctas;
-        if (s > ksteps / 8) s = ksteps / 8;
-        if (s > 8) s = 8;
+        if (s > ksteps / 16) s = ksteps / 16;
+        if (s > 4) s = 4;
         const int64_t need = 65536 * 4 + (int64_t)ctas * s * 128 * BN * 4;
         if (s >= 2 && need <= a->workspace_bytes && ctas <= 65536) p.splits = s;
     }
+    if (f_split > 0 && a->workspace && ctas <= 65536 && 65536 * 4 + (int64_t)ctas * f_split * 128 * BN * 4 <= a->workspace_bytes)
+        p.splits = f_split > ksteps ? ksteps : f_split;
     p.ksteps_per_split = (ksteps + p.splits - 1) / p.splits;
     p.splits = (ksteps + p.ksteps_per_split - 1) / p.ksteps_per_split;
     p.ws_counter = (int*)a->workspace;
     p.ws_partial = a->workspace ? (float*)((char*)a->workspace + 65536 * 4) : nullptr;
     // pipeline depth: short K loops want several co-resident CTAs per SM (2 stages -> 3 CTAs/SM); long K loops on
     // small grids want a deep ring to cover the L2 latency (6 stages, 1 CTA/SM); big grids take 3 stages (2 CTAs/SM).
-    const int depth = (p.ksteps_per_split <= 4) ? 2 : ((ctas * p.splits < 2 * sms) ? 6 : 3);
+    int depth = (p.ksteps_per_split <= 4) ? 2 : ((ctas * p.splits < 2 * sms) ? 6 : 3);
+    if (f_depth == 2 || f_depth == 3 || f_depth == 6) depth = f_depth;
     if (BN == 128) {
         if (depth == 2) return launch_conv<128, 2>(maps, p, a->cout_pad, stream);
         if (depth == 3) return launch_conv<128, 3>(maps, p, a->cout_pad, stream);

@@ -113,6 +113,22 @@ class InferenceCore:
                     self.last_deep_update_ti = self.curr_ti
                     return unpad(prob, self.pad)
 
+        if (self.use_cuda_graph and mask is not None and not need_segment and is_mem_frame and not disable_memory_updates
+                and not return_key_and_stuff and image.is_cuda and mask.shape[0] == len(self.all_labels)
+                and (is_deep_update == self.deep_update_sync)):
+            # fully annotated frame: encode_key -> aggregate(mask) -> encode_value, replayed from a recorded graph
+            mask_p, _ = pad_divide_by(mask, 16)
+            self.memory.create_hidden_state(len(self.all_labels), image[..., ::16, ::16])
+            g = self._encode_graph(image, mask_p, deep=is_deep_update)
+            if g is not None:
+                self.memory.add_memory(g['key'], g['shrinkage'], g['value'], self.all_labels,
+                                       selection=g['selection'] if self.enable_long_term else None, ignore=do_not_add_mask_to_memory)
+                self.last_mem_ti = self.curr_ti
+                if is_deep_update:
+                    self.memory.set_hidden(g['hidden_out'].clone())
+                    self.last_deep_update_ti = self.curr_ti
+                return unpad(g['pred'], self.pad)
+
         key, shrinkage, selection, f16, f8, f4 = self.network.encode_key(
             image, need_ek=(self.enable_long_term or need_segment), need_sk=True)
 
@@ -240,9 +256,63 @@ class InferenceCore:
             print(f'[xmem2_b200] recorded {"memory" if mem_frame else "ordinary"}-frame graph in {time.perf_counter() - t0:.3f}s', flush=True)
         return g
 
+    def _encode_graph(self, image, mask_padded, deep):
+        """encode_key -> aggregate(mask) -> encode_value for a fully annotated frame (inference_core.py:128-137,157-167),
+        replayed from a recorded CUDA graph.  Independent of the memory banks, so one graph per (shape, #objects, deep)
+        serves every video on this network.  deep=True also runs the HiddenReinforcer on the current hidden state.
+        Returns the dict of static outputs, or None on the first (warm-up) call of a signature."""
+        n = mask_padded.shape[0]
+        sig = (tuple(image.shape), n, 'enc', bool(deep))
+        g = _GRAPH_CACHE.get((id(self.network), sig))
+        if g is None:
+            if sig not in self._graph_warm:
+                self._graph_warm.add(sig)
+                return None
+            net, mem, dev = self.network, self.memory, image.device
+            h, w = image.shape[-2] // 16, image.shape[-1] // 16
+            g = {'image': image.clone(), 'mask': mask_padded.clone().float()}
+            if deep:
+                g['hidden_in'] = torch.zeros((1, n, h, w, mem.hidden_dim), device=dev).permute(0, 1, 4, 2, 3)
+                g['hidden_out'] = torch.zeros((1, n, h, w, mem.hidden_dim), device=dev).permute(0, 1, 4, 2, 3)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            launches0 = lib.load().xm_launch_count()
+            with torch.cuda.graph(graph):
+                key, shrinkage, selection, f16, _, _ = net.encode_key(g['image'], need_ek=True, need_sk=True)
+                pred = aggregate(g['mask'], dim=0)
+                value, hidden = net.encode_value(g['image'], f16, g.get('hidden_in'), pred[1:].unsqueeze(0), is_deep_update=deep)
+                if deep:
+                    g['hidden_out'].copy_(hidden)
+                g.update(key=key, shrinkage=shrinkage, selection=selection, value=value, pred=pred)
+            g['graph'] = graph
+            g['launches'] = int(lib.load().xm_launch_count() - launches0)
+            lib.load().xm_add_launch_count(-g['launches'])
+            if len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
+                _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
+            _GRAPH_CACHE[(id(self.network), sig)] = g
+        g['image'].copy_(image)
+        g['mask'].copy_(mask_padded)
+        if deep:
+            g['hidden_in'].copy_(self.memory.get_hidden())
+        g['graph'].replay()
+        lib.load().xm_add_launch_count(g['launches'])
+        return g
+
     def put_to_permanent_memory(self, image, mask, ti=None):
         """encode an annotated frame straight into permanent memory (inference_core.py:154-179)."""
         image = self._prepare(image)
+        if self.use_cuda_graph and image.is_cuda and mask.shape[0] == len(self.all_labels):
+            mask_p, _ = pad_divide_by(mask, 16)
+            g = self._encode_graph(image, mask_p, deep=False)
+            if g is not None:
+                self.memory.create_hidden_state(len(self.all_labels), g['key'])
+                sel = g['selection'] if self.enable_long_term else None
+                is_update = self.memory.frame_already_saved(ti)
+                if is_update:
+                    self.memory.update_permanent_memory(ti, g['key'], g['shrinkage'], g['value'], selection=sel)
+                else:
+                    self.memory.add_memory(g['key'], g['shrinkage'], g['value'], self.all_labels, selection=sel, permanent=True, ti=ti)
+                return is_update
         key, shrinkage, selection, f16, _, _ = self.network.encode_key(image, need_ek=True, need_sk=True)
         mask, _ = pad_divide_by(mask, 16)
         pred_prob_with_bg = aggregate(mask, dim=0)
