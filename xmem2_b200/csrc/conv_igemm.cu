@@ -30,6 +30,8 @@ namespace {
 struct alignas(64) ConvMaps {
     CUtensorMap a[3];
     CUtensorMap w;
+    CUtensorMap o;      // output   [out_stride, Wo, Ho, B]   box [64, TW, TH, 1]   (TMA-store epilogue)
+    CUtensorMap r;      // residual [cout, Wo, Ho, B|1]       box [64, TW, TH, 1]
 };
 
 struct ConvP {
@@ -52,6 +54,7 @@ struct ConvP {
     int splits, ksteps_per_split;     // split-K: blockIdx.z owns k-steps [z*kps, min((z+1)*kps, ksteps))
     float* ws_partial;                // [tile][split][128][BN] fp32
     int* ws_counter;                  // [tile] arrival counters (zero before and after every launch)
+    int tma_epilogue;                 // 1: stage the tile in swizzled smem, residual in / output out through TMA
 };
 
 template <int BN, int CONV_STAGES>
@@ -61,6 +64,7 @@ struct ConvSmem {
     alignas(8) uint64_t full[CONV_STAGES];
     uint64_t empty[CONV_STAGES];
     uint64_t done;
+    uint64_t resbar;
     uint32_t tmem_base;
     int is_last;
     float bias[BN];
@@ -92,6 +96,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < CONV_STAGES; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
         mbar_init(&sm.done, 1);
+        mbar_init(&sm.resbar, 1);
         fence_mbar_init();
     }
     if (warp == 1) { tmem_alloc(&sm.tmem_base, BN); tmem_relinquish(); }
@@ -185,6 +190,81 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (!sm.is_last) goto teardown;
             __threadfence();
+        }
+        if (p.tma_epilogue) {
+            // Stage buffers are free now (every MMA has completed): a[] holds the output tile, b[] the residual tile,
+            // both as 64-channel boxes of 128 pixel rows x 128 B with the 128-byte swizzle (conflict-free 16-B accesses).
+            uint8_t* stage_out = &sm.a[0][0];
+            uint8_t* stage_res = &sm.b[0][0];
+            const int nbox = min(BN / 64, (p.cout - n0) / 64);        // cout is a multiple of 64 on this path
+            if (p.residual && threadIdx.x == 64) {
+                mbar_expect_tx(&sm.resbar, nbox * 128 * 128);
+                for (int k = 0; k < nbox; ++k)
+                    tma_load_4d(stage_res + k * 128 * 128, &maps.r, &sm.resbar, n0 + 64 * k, x0, y0, p.residual_bcast ? 0 : b);
+            }
+#pragma unroll 1
+            for (int k = 0; k < nbox; ++k) {
+                float v[64];
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    const int c0 = 64 * k + 32 * hlf;
+                    if (p.splits > 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[32 * hlf + j] = 0.f;
+                        for (int z = 0; z < p.splits; ++z) {
+                            const float* src = p.ws_partial + (((size_t)tile_lin * p.splits + z) * 128 + row) * BN + c0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 f = __ldcg(reinterpret_cast<const float4*>(src + j));
+                                v[32 * hlf + j] += f.x; v[32 * hlf + j + 1] += f.y; v[32 * hlf + j + 2] += f.z; v[32 * hlf + j + 3] += f.w;
+                            }
+                        }
+                    } else {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(lane_base) << 16) + c0, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[32 * hlf + j] = __uint_as_float(r[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[32 * hlf + j] += sm.bias[c0 + j];
+                }
+                if (p.residual) {
+                    if (k == 0) mbar_wait(&sm.resbar, 0, 24);
+                    const uint8_t* rrow = stage_res + k * 128 * 128 + row * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(rrow + ((c ^ (row & 7)) << 4));
+                        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __half22float2(h2[e]);
+                            v[8 * c + 2 * e] += f.x; v[8 * c + 2 * e + 1] += f.y;
+                        }
+                    }
+                }
+                uint8_t* orow = stage_out + k * 128 * 128 + row * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    uint4 u;
+                    if (p.relu) {
+                        u.x = pack_half2(fmaxf(v[8 * c], 0.f), fmaxf(v[8 * c + 1], 0.f)); u.y = pack_half2(fmaxf(v[8 * c + 2], 0.f), fmaxf(v[8 * c + 3], 0.f));
+                        u.z = pack_half2(fmaxf(v[8 * c + 4], 0.f), fmaxf(v[8 * c + 5], 0.f)); u.w = pack_half2(fmaxf(v[8 * c + 6], 0.f), fmaxf(v[8 * c + 7], 0.f));
+                    } else {
+                        u.x = pack_half2(v[8 * c], v[8 * c + 1]); u.y = pack_half2(v[8 * c + 2], v[8 * c + 3]);
+                        u.z = pack_half2(v[8 * c + 4], v[8 * c + 5]); u.w = pack_half2(v[8 * c + 6], v[8 * c + 7]);
+                    }
+                    *reinterpret_cast<uint4*>(orow + ((c ^ (row & 7)) << 4)) = u;
+                }
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) {
+                for (int k = 0; k < nbox; ++k) tma_store_4d(&maps.o, stage_out + k * 128 * 128, p.out_offset + n0 + 64 * k, x0, y0, b);
+                tma_store_commit();
+                tma_store_wait_read();
+            }
+            goto teardown;
         }
         const bool vec_ok = (p.out_stride % 8 == 0) && (p.out_offset % 8 == 0) && (p.residual_stride % 8 == 0);
 #pragma unroll 1
@@ -368,6 +448,24 @@ extern "C" int xm_conv2d_nhwc(const xm_conv_args_t* a, void* stream_) {
         uint64_t st[1] = {K * 2};
         uint32_t bx[2] = {64, (uint32_t)BN};
         if (xm_make_tmap_f16(&maps.w, a->weight, 2, d, st, bx)) return XM_ERR_CUDA;
+    }
+    // TMA epilogue: whole 64-channel boxes, a single plain output (no second ReLU'd copy), 16-byte aligned channel offsets
+    p.tma_epilogue = (a->cout % 64 == 0 && a->out && !a->out_relu && a->out_offset % 8 == 0 && a->out_stride % 8 == 0) ? 1 : 0;
+    {
+        const void* obase = p.tma_epilogue ? a->out : a->src[0].ptr;
+        const uint64_t OC = p.tma_epilogue ? (uint64_t)a->out_stride : (uint64_t)a->src[0].channels;
+        const uint64_t OW = p.tma_epilogue ? (uint64_t)p.Wo : (uint64_t)a->W, OH = p.tma_epilogue ? (uint64_t)p.Ho : (uint64_t)a->H;
+        uint64_t d[4] = {OC, OW, OH, (uint64_t)(p.tma_epilogue ? a->batch : 1)};
+        uint64_t st[3] = {OC * 2, OW * OC * 2, OH * OW * OC * 2};
+        uint32_t bx[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
+        if (xm_make_tmap_f16(&maps.o, obase, 4, d, st, bx)) return XM_ERR_CUDA;
+        if (p.tma_epilogue && a->residual) {
+            uint64_t dr[4] = {(uint64_t)a->cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)(a->residual_broadcast ? 1 : a->batch)};
+            uint64_t sr[3] = {(uint64_t)a->cout * 2, (uint64_t)p.Wo * a->cout * 2, (uint64_t)p.Ho * p.Wo * a->cout * 2};
+            if (xm_make_tmap_f16(&maps.r, a->residual, 4, dr, sr, bx)) return XM_ERR_CUDA;
+        } else {
+            maps.r = maps.o;
+        }
     }
     // occupancy plan: many CTAs -> 3 stages (2 CTAs/SM overlap prologue/epilogue); few CTAs -> 6 stages (hide L2
     // latency in the k-loop) and split-K over blockIdx.z so that idle SMs share the reduction.
