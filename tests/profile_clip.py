@@ -14,7 +14,8 @@ dev = 'cuda:0'
 net = XMem(dict(bench.CFG), None).to(dev).eval(); net.load_weights(synth_state_dict(0))
 frames, masks = bench.clip_inputs(1234)
 frames = frames.to(dev); masks = {k: v.to(dev) for k, v in masks.items()}
-fac = lambda: InferenceCore(net, dict(bench.CFG))
+cfg = dict(bench.CFG); cfg['use_cuda_graph'] = False      # eager launches so that ncu sees every kernel individually
+fac = lambda: InferenceCore(net, dict(cfg))
 bench.run_clip(fac, frames[:12], {0: masks[0]}, dev, False)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()

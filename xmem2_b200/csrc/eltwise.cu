@@ -67,6 +67,45 @@ __global__ void im2col_stem_kernel(const float* __restrict__ image, const float*
     }
 }
 
+// Key-encoder stem (3 image channels): K layout k = kh*24 + kw*3 + c (kw<7, c<3; 3 zero slots per kernel row, rows 7 is all
+// zero -> 192).  One thread builds one (pixel, kernel row) = 24 halfs = three 16-byte stores.
+__global__ void im2col_stem3_kernel(const float* __restrict__ image, int H, int W, __half* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int Ho = H / 2, Wo = W / 2;
+    const size_t total = (size_t)Ho * Wo * 8;
+    const size_t plane = (size_t)H * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int kh = i & 7;
+        const size_t p = i >> 3;
+        const int xo = p % Wo, yo = p / Wo;
+        float v[24];
+#pragma unroll
+        for (int e = 0; e < 24; ++e) v[e] = 0.f;
+        const int y = 2 * yo + kh - 3;
+        if (kh < 7 && y >= 0 && y < H) {
+            const int xb = 2 * xo - 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* rowp = image + c * plane + (size_t)y * W;
+#pragma unroll
+                for (int kw = 0; kw < 7; ++kw) {
+                    const int x = xb + kw;
+                    if (x >= 0 && x < W) v[kw * 3 + c] = __ldg(rowp + x);
+                }
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + p * 192 + kh * 24);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            uint4 u;
+            u.x = tc5::pack_half2(v[8 * q], v[8 * q + 1]); u.y = tc5::pack_half2(v[8 * q + 2], v[8 * q + 3]);
+            u.z = tc5::pack_half2(v[8 * q + 4], v[8 * q + 5]); u.w = tc5::pack_half2(v[8 * q + 6], v[8 * q + 7]);
+            dst[q] = u;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- maxpool 3x3 s2 p1 (8 channels / thread)
 __global__ void maxpool_kernel(const __half* __restrict__ in, int B, int H, int W, int C, int relu, __half* __restrict__ out) {
     pdl_wait();
@@ -191,6 +230,7 @@ __global__ void cbam_mlp_kernel(const float* __restrict__ psum, const float* __r
     const int b = blockIdx.x, t = threadIdx.x;
     {
         float s = 0.f, m = -INFINITY;
+#pragma unroll
         for (int sl = 0; sl < CBAM_SLICES; ++sl) {
             s += psum[((size_t)b * CBAM_SLICES + sl) * C + t];
             m = fmaxf(m, pmax[((size_t)b * CBAM_SLICES + sl) * C + t]);
@@ -203,14 +243,16 @@ __global__ void cbam_mlp_kernel(const float* __restrict__ psum, const float* __r
     for (int u = warp; u < 2 * R; u += nwarps) {
         const int r = u % R; const float* in = (u < R) ? in0 : in1;
         float a = 0.f;
-        for (int c = lane; c < C; c += 32) a += w1[(size_t)r * C + c] * in[c];
+#pragma unroll 8
+        for (int c = lane; c < C; c += 32) a += __ldg(w1 + (size_t)r * C + c) * in[c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if (lane == 0) (u < R ? h0 : h1)[r] = fmaxf(a + b1[r], 0.f);
     }
     __syncthreads();
     float a = 2.f * b2[t];
-    for (int r = 0; r < R; ++r) a += w2[(size_t)t * R + r] * (h0[r] + h1[r]);
+#pragma unroll 8
+    for (int r = 0; r < R; ++r) a += __ldg(w2 + (size_t)t * R + r) * (h0[r] + h1[r]);
     scale[(size_t)b * C + t] = sigmoidf_(a);
 }
 // (c) per pixel: max and mean over channels of x * scale_c.  One warp per pixel.
@@ -339,38 +381,52 @@ __global__ void area_down_kernel(const __half* __restrict__ in, const __half* __
 }
 
 // ---------------------------------------------------------------- single-output 3x3 convolution (decoder.pred, modules.py:227,239)
-// logits[b][y][x] = bias + sum_{tap,c} w[tap][c] * in[b][y+dy][x+dx][c].  One warp per output pixel, lanes split channels.
+// logits[b][y][x] = bias + sum_{tap,c} w[tap][c] * in[b][y+dy][x+dx][c].  One block = 8x8 output pixels: the 10x10xC halo
+// tile is staged in shared memory once (instead of 9 L2 reads per pixel); one warp per output row, lanes split channels.
 __global__ void conv3x3_c1_kernel(const __half* __restrict__ in, const __half* __restrict__ wgt, float bias, int B, int H, int W, int C,
                                   __half* __restrict__ out) {
     pdl_wait();
     pdl_launch_dependents();
-    extern __shared__ __half wsm[];                  // [9][C]
-    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) wsm[i] = wgt[i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const size_t npix = (size_t)B * H * W;
+    extern __shared__ uint4 tile_sm[];               // [10][10][C/8] uint4
     const int C8 = C / 8;
-    for (size_t pix = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += (size_t)gridDim.x * (blockDim.x >> 5)) {
-        const int x = pix % W, y = (pix / W) % H, b = pix / ((size_t)H * W);
-        float acc = 0.f;
-        for (int tap = 0; tap < 9; ++tap) {
-            const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const uint4* src = reinterpret_cast<const uint4*>(in + (((size_t)b * H + yy) * W + xx) * C);
-            const uint4* wv = reinterpret_cast<const uint4*>(wsm + tap * C);
-            for (int c8 = lane; c8 < C8; c8 += 32) {
-                const uint4 a = __ldg(src + c8), ww = wv[c8];
-                const __half2* ha = reinterpret_cast<const __half2*>(&a); const __half2* hw2 = reinterpret_cast<const __half2*>(&ww);
+    const int tiles_x = (W + 7) / 8, tiles_y = (H + 7) / 8;
+    int t = blockIdx.x;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y; const int b = t / tiles_y;
+    const int x0 = tx * 8 - 1, y0 = ty * 8 - 1;
+    for (int i = threadIdx.x; i < 100 * C8; i += blockDim.x) {
+        const int c8 = i % C8, px = (i / C8) % 10, py = i / (C8 * 10);
+        const int y = y0 + py, x = x0 + px;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * H + y) * W + x) * C) + c8);
+        tile_sm[i] = v;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;       // 8 warps: warp = output row inside the patch
+    // this lane's weights: channels lane*8 .. +7 of every tap (C8 == 32 for the decoder)
+    for (int c8 = lane; c8 < C8; c8 += 32) {
+        uint4 wv[9];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) wv[tap] = __ldg(reinterpret_cast<const uint4*>(wgt + tap * C) + c8);
+        for (int px = 0; px < 8; ++px) {
+            float acc = 0.f;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const uint4 a = tile_sm[((warp + tap / 3) * 10 + px + tap % 3) * C8 + c8];
+                const __half2* ha = reinterpret_cast<const __half2*>(&a); const __half2* hw2 = reinterpret_cast<const __half2*>(&wv[tap]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float2 fa = __half22float2(ha[e]), fw = __half22float2(hw2[e]);
                     acc += fa.x * fw.x + fa.y * fw.y;
                 }
             }
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) out[pix] = __float2half_rn(acc + bias);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            const int y = ty * 8 + warp, x = tx * 8 + px;
+            if (lane == 0 && y < H && x < W) {
+                if (c8 < 32) out[((size_t)b * H + y) * W + x] = __float2half_rn(acc + bias);
+            }
+        }
     }
 }
 
@@ -462,6 +518,12 @@ extern "C" int xm_im2col_stem(const float* image, const float* masks, int32_t n,
     XM_REQUIRE(image && out && n >= 1 && H % 2 == 0 && W % 2 == 0, "xm_im2col_stem: bad arguments");
     const int C = masks ? 5 : 3;
     XM_REQUIRE(kpad >= 49 * C && kpad % 64 == 0, "xm_im2col_stem: kpad must be a multiple of 64 >= %d", 49 * C);
+    if (!masks && n == 1 && kpad == 192) {        // key-encoder stem: row-padded K layout (kh*24 + kw*3 + c)
+        const size_t tot = (size_t)(H / 2) * (W / 2) * 8;
+        XM_CHECK_CUDA(tc5_launch(im2col_stem3_kernel, dim3(grid_for(tot)), dim3(256), 0, STREAM, image, H, W, (__half*)out));
+        xm_count_launches(1);
+        return XM_OK;
+    }
     const size_t total = (size_t)n * (H / 2) * (W / 2) * (kpad / 8);
     XM_CHECK_CUDA(tc5_launch(im2col_stem_kernel, dim3(grid_for(total)), dim3(256), 0, STREAM, image, masks, n, H, W, C, kpad, (__half*)out));
     xm_count_launches(1);
@@ -539,12 +601,15 @@ extern "C" int xm_area_down(const void* in, const void* extra, int32_t B, int32_
 
 extern "C" int xm_conv3x3_c1(const void* in, const void* weight_tap_c, float bias, int32_t B, int32_t H, int32_t W, int32_t C, void* out,
                              void* stream) {
-    XM_REQUIRE(in && weight_tap_c && out && C % 8 == 0 && C <= 1024, "xm_conv3x3_c1: bad arguments");
-    const size_t npix = (size_t)B * H * W;
-    int blocks = (int)((npix + 7) / 8);
-    const int cap = xm_num_sms() * 8;
-    if (blocks > cap) blocks = cap;
-    XM_CHECK_CUDA(tc5_launch(conv3x3_c1_kernel, dim3(blocks), dim3(256), (size_t)9 * C * 2, STREAM, (const __half*)in, (const __half*)weight_tap_c,
+    XM_REQUIRE(in && weight_tap_c && out && C == 256, "xm_conv3x3_c1: specialised for C = 256 (decoder.pred)");
+    const int blocks = B * ((H + 7) / 8) * ((W + 7) / 8);
+    const size_t smem = (size_t)100 * (C / 8) * 16;
+    static bool attr_done = false;
+    if (!attr_done) {
+        XM_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_c1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    XM_CHECK_CUDA(tc5_launch(conv3x3_c1_kernel, dim3(blocks), dim3(256), smem, STREAM, (const __half*)in, (const __half*)weight_tap_c,
                              bias, B, H, W, C, (__half*)out));
     xm_count_launches(1);
     return XM_OK;

@@ -138,7 +138,13 @@ class XMem(nn.Module):
 
         def put_stem(key, conv, bn, kpad):
             w, b = self._folded(conv, bn)                         # [64, C, 7, 7]
-            flat = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)  # k = (kh*7+kw)*C + c, matches xm_im2col_stem
+            if w.shape[1] == 3:
+                # key stem: k = kh*24 + kw*3 + c (each kernel row padded to 24), matches im2col_stem3_kernel
+                rows = torch.zeros((w.shape[0], 8, 24))
+                rows[:, :7, :21] = w.permute(0, 2, 3, 1).reshape(w.shape[0], 7, 21)
+                flat = rows.reshape(w.shape[0], 192)
+            else:
+                flat = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)  # k = (kh*7+kw)*C + c, matches xm_im2col_stem
             put(key, flat[:, :, None, None], b, cin_pad=kpad)
 
         put_stem('key_encoder.conv1', 'key_encoder.conv1', 'key_encoder.bn1', 192)
