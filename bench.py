@@ -153,8 +153,13 @@ def k1_roofline(device):
     except Exception:
         pass
     peak = peaks.get('bf16_tflops', 1590.0)
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the six kernels of one call, from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(REPO, 'profiles', 'r1_k1_traffic.json')))['dram_bytes_per_call']
+    except Exception:
+        pass
     return {'bound': 'tensor', 'achieved': round(flops / t / 1e12, 2), 'peak': peak, 'unit': 'TFLOP/s',
-            'frac': round(flops / t / 1e12 / peak, 4), 'traffic': None, 'kernel': 'xm_affinity_readout (pass1+merge+pass2+finish)',
+            'frac': round(flops / t / 1e12 / peak, 4), 'traffic': traffic, 'kernel': 'xm_affinity_readout (pass1+merge+pass2+finish)',
             'launch_us': round(t * 1e6, 1), 'shape': {'N': N, 'HW': hw, 'n_obj': 1},
             'peak_source': 'MEASURED_PEAKS.json bf16 burst' if peaks else 'fallback', 'algorithmic_bytes': bytes_,
             'hbm_gbs_if_bytes_bound': round(bytes_ / t / 1e9, 1)}
