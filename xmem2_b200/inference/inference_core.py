@@ -21,11 +21,19 @@ from ..util.tensor_util import pad_divide_by, unpad
 from .memory_manager import MemoryManager
 
 
-# recorded frame graphs are shared by every InferenceCore built on the same network (one per video in the reference
-# driver): key = (id(network), signature); value = graph + its static buffers.  Arena recycling in KeyValueMemoryStore
-# makes consecutive videos of the same shape hit the same signature.
-_GRAPH_CACHE = {}
+# Recorded frame graphs are shared by every InferenceCore built on the same network (the reference driver builds one
+# core per video): they live in a dict attached to the network object (so they die with its weights), keyed by the
+# graph signature; value = graph + its static buffers.  Arena recycling in KeyValueMemoryStore makes consecutive videos
+# of the same shape hit the same signature.
 _GRAPH_CACHE_MAX = 8
+
+
+def _graph_cache(network) -> dict:
+    cache = network.__dict__.get('_xm_graph_cache')
+    if cache is None:
+        cache = {}
+        network.__dict__['_xm_graph_cache'] = cache
+    return cache
 
 
 class InferenceCore:
@@ -187,15 +195,16 @@ class InferenceCore:
         sig = (tuple(image.shape), mem.layout_signature(), len(self.all_labels), bool(mem_frame))
         g = self._graphs.get(sig)
         if g is None:
-            g = _GRAPH_CACHE.get((id(self.network), sig))
+            cache = _graph_cache(self.network)
+            g = cache.get(sig)
             if g is None:
                 if sig not in self._graph_warm:
                     self._graph_warm.add(sig)           # run this frame eagerly, record on the next one
                     return None
                 g = self._capture(image, mem_frame)
-                if len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
-                    _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
-                _GRAPH_CACHE[(id(self.network), sig)] = g
+                if len(cache) >= _GRAPH_CACHE_MAX:
+                    cache.pop(next(iter(cache)))
+                cache[sig] = g
             self._graphs = {sig: g, **{k: v for k, v in self._graphs.items() if k[:3] == sig[:3]}}
         # the graph's hidden-state buffer is shared by every core using this graph: hand the previous user its own copy
         g_hidden = g['hidden']
@@ -263,7 +272,8 @@ class InferenceCore:
         Returns the dict of static outputs, or None on the first (warm-up) call of a signature."""
         n = mask_padded.shape[0]
         sig = (tuple(image.shape), n, 'enc', bool(deep))
-        g = _GRAPH_CACHE.get((id(self.network), sig))
+        cache = _graph_cache(self.network)
+        g = cache.get(sig)
         if g is None:
             if sig not in self._graph_warm:
                 self._graph_warm.add(sig)
@@ -287,9 +297,9 @@ class InferenceCore:
             g['graph'] = graph
             g['launches'] = int(lib.load().xm_launch_count() - launches0)
             lib.load().xm_add_launch_count(-g['launches'])
-            if len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
-                _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
-            _GRAPH_CACHE[(id(self.network), sig)] = g
+            if len(cache) >= _GRAPH_CACHE_MAX:
+                cache.pop(next(iter(cache)))
+            cache[sig] = g
         g['image'].copy_(image)
         g['mask'].copy_(mask_padded)
         if deep:
