@@ -72,3 +72,22 @@ def test_planted_cluster_overflows_candidate_lists():
     planted = list(range(128, 160)) + list(range(192, 210))
     case['banks'][1]['key'][planted] = (q0[None, :] + 0.05 * torch.randn(len(planted), 64, generator=g)).half()
     _check(case, max_ambiguous=400)     # near-identical planted columns produce near-ties at rank 30 by construction
+
+
+def test_full_size_1080p_partition_of_unity():
+    # BASELINE.json config-4 scale on one GPU (HW = 8160 queries, 5 working frames + 1 permanent = 48 960 columns):
+    # size-independent properties instead of an oracle run — with all values == 1 the readout must be exactly the sum of
+    # the affinity weights (== 1 for every query and channel), and the usage column sums must add up to the number of
+    # queries (every affinity column of do_softmax sums to 1, model/memory_util.py:49,63).
+    import torch
+    hw = 8160
+    case = k1_ref.make_case(hw=hw, sizes=(0, 5 * hw, hw), n_obj=1, group_begins=[(0, 1, [0, 0, 0])], seed=9)
+    for b in case['banks']:
+        if b is not None:
+            b['val'][:, :, :b['n']] = 1.0
+    out_chw, out_hwc, usage_bufs, _ = k1_ref.run_kernel(case)
+    assert torch.isfinite(out_chw).all()
+    assert (out_chw.float() - 1.0).abs().max().item() < 4e-3          # 30 fp16-rounded weights summed in fp32
+    assert torch.equal(out_hwc.transpose(1, 2), out_chw)
+    total = sum(float(u.sum()) for u in usage_bufs if u is not None)
+    assert abs(total - hw) < 1e-2 * hw
