@@ -45,7 +45,7 @@ def clip_inputs(seed, n_frames=N_FRAMES):
     return frames, masks
 
 
-def run_clip(core_factory, frames, masks, device, host_io, sync_each=False):
+def run_clip(core_factory, frames, masks, device, host_io):
     """One step: preload permanent memory, then the frame loop (run_on_video.py:65-112 without file IO)."""
     core = core_factory()
     core.set_all_labels([1])
@@ -212,8 +212,6 @@ def main():
             v = oracle_fps('cpu', nfr, threads=cores)
             if i >= args.warmup:
                 vals.append(v)
-            if i == 0 and args.warmup + args.steps > 3:      # keep the whole arm within a few minutes
-                pass
         fps = sum(vals) / len(vals)
         line = {'impl': 'reference', 'metric': 'fps_480p', 'value': round(fps, 4), 'unit': 'frames/s', 'n_gpus': args.gpus,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(1000 * nfr / fps, 2), 'higher_is_better': True,

@@ -67,11 +67,6 @@ __device__ __forceinline__ void locate_tile(const K1Seg& sg, int t, int& s, int&
     hi = min(TN, sg.end[s] - col);
 }
 
-__device__ __forceinline__ float score(uint32_t acc_bits, float bsq, float ms) {
-    // (S' - b_sq) * shrinkage / sqrt(CK)   memory_util.py:27,35 (CK = 64 -> exact *0.125)
-    return (__uint_as_float(acc_bits) - bsq) * ms * 0.125f;
-}
-
 __device__ __forceinline__ float fast_exp(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * LOG2E));

@@ -37,14 +37,11 @@ _ARENA_POOL_MAX = 8
 
 
 class KeyValueMemoryStore:
-    def __init__(self, count_usage: bool, reserve: int = 0, right_aligned_groups: bool = False):
+    def __init__(self, count_usage: bool, reserve: int = 0):
         self.count_usage = count_usage
         self.obj_groups: List[List[int]] = []
         self.all_objects: List[int] = []
         self._reserve = reserve
-        # long-term memory stores a later group's values compactly against the LAST columns
-        # (reference memory_manager.py:99-103 reads `similarity[:, -get_v_size(gi):]`)
-        self._right_aligned = right_aligned_groups
         self._n = 0
         self._cap = 0
         self._engaged = False

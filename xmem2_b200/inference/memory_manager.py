@@ -9,7 +9,6 @@ with no bank concatenation and no N x HW intermediate.  The banks are arena-back
 from __future__ import annotations
 
 import ctypes as C
-import math
 import warnings
 
 import torch
@@ -96,8 +95,8 @@ class MemoryManager:
         return banks, groups, n_obj, self.top_k
 
     def refresh_plan(self, device, disable_usage_updates=False):
-        """(Re)compute the column-range plan when any bank size / group range / usage routing changed and copy it to
-        the head of the workspace (stream ordered).  Returns the args struct for the kernel call."""
+        """Bank/group description for the kernel call plus the key that tells whether the device-side plan (column
+        ranges, usage routing) is stale."""
         a, n_obj, use_long = self._read_args()
         if disable_usage_updates or not self.enable_long_term:
             for i in range(3):
@@ -105,10 +104,6 @@ class MemoryManager:
         key = (tuple((a.banks[i].keys, a.banks[i].shrinkage, a.banks[i].values, a.banks[i].usage, a.banks[i].cap, a.banks[i].size)
                      for i in range(3)),
                tuple((a.groups[g].obj_begin, a.groups[g].n_obj, tuple(a.groups[g].begin)) for g in range(a.n_groups)), self.top_k)
-        if self.HW is not None:
-            wsb = lib.load().xm_affinity_workspace_bytes(self.HW, n_obj)
-        else:
-            wsb = 0
         return a, n_obj, use_long, key
 
     def _ensure_ws(self, hw, n_obj, device):
