@@ -38,10 +38,9 @@ def _nchw_view(t: Tensor) -> Tensor:
 class XMem(nn.Module):
     def __init__(self, config, model_path=None, map_location=None, pretrained_key_encoder=True, pretrained_value_encoder=True):
         super().__init__()
-        if pretrained_key_encoder or pretrained_value_encoder:
-            # the reference downloads ImageNet ResNet weights here (model/resnet.py:154-164); there is no
-            # network on a B200 serving box, weights always come from `load_weights` / `model_path`.
-            pass
+        # pretrained_*_encoder are accepted for signature compatibility only: the reference downloads ImageNet ResNet
+        # weights for them (model/resnet.py:154-164); here weights always come from `model_path` / `load_weights`.
+        del pretrained_key_encoder, pretrained_value_encoder
         model_weights = self.init_hyperparameters(config, model_path, map_location)
         self.single_object = config.get('single_object', False)
         if self.single_object:
