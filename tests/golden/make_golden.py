@@ -163,8 +163,51 @@ def run_clip(XMem, InferenceCore, name, H, W, n_frames, n_obj, annotated, first_
     print(f'clip {name}: oracle-vs-reference max prob err {maxerr:.2e} mean {meanerr:.2e}; final sizes {sizes[-1]}')
 
 
+def golden_chair(XMem, InferenceCore):
+    """BASELINE.json config 1: the reference's own example clip (example_videos/chair) through the reference's own reader
+    (inference/data/video_reader.py) at size=160, frame 0 annotated and preloaded, 8 frames, CPU.  Inputs are stored as the
+    fp16-rounded normalised tensors the reader produced, so no image decoding is needed to replay them."""
+    from inference.data.video_reader import VideoReader
+    from inference.data.mask_mapper import MaskMapper
+    root = os.path.join(REF, 'example_videos', 'chair')
+    reader = VideoReader('', os.path.join(root, 'JPEGImages'), os.path.join(root, 'Annotations'), size=160, use_all_masks=True)
+    mapper = MaskMapper()
+    n_frames = 8
+    rgbs = [reader[i].rgb.half() for i in range(n_frames)]
+    s0 = reader[0]
+    msk, labels = mapper.convert_mask(s0.mask, exhaustive=True)
+    msk = torch.Tensor(msk)
+    if s0.need_resize:
+        msk = reader.resize_mask(msk.unsqueeze(0))[0]
+    state = synth_state_dict(0)
+    cfg = base_cfg(mem_every=3)
+    net, core = make_ref_core(XMem, InferenceCore, dict(cfg), state)
+    ocore = O.OracleCore(O.OracleNet(state), dict(cfg))
+    all_labels = list(mapper.remappings.values())
+    for c in (core, ocore):
+        c.set_all_labels(all_labels)
+        c.put_to_permanent_memory(rgbs[0].float(), msk.clone())
+    probs, err = [], 0.0
+    for ti in range(n_frames):
+        m = msk.clone() if ti == 0 else None
+        kw = dict(end=(ti == n_frames - 1), do_not_add_mask_to_memory=m is not None)
+        p = core.step(rgbs[ti].float(), m, list(labels) if m is not None else None, **kw)
+        po = ocore.step(rgbs[ti].float(), m.clone() if m is not None else None, list(labels) if m is not None else None, **kw)
+        err = max(err, (p - po).abs().mean().item())
+        probs.append(p.numpy().astype(np.float16))
+    assert err < 2e-4, err
+    np.savez_compressed(os.path.join(HERE, 'clip_chair.npz'), rgb=torch.stack(rgbs).numpy(), mask0=msk.numpy().astype(np.uint8),
+                        probs=np.stack(probs), labels=np.array(all_labels), mem_every=np.array(3),
+                        temp_size=np.array(core.memory.temporary_work_mem.size), perm_size=np.array(core.memory.permanent_work_mem.size))
+    print(f'chair golden ok: {tuple(rgbs[0].shape)} frames={n_frames} oracle-vs-reference mean err {err:.2e}; '
+          f'temp={core.memory.temporary_work_mem.size} perm={core.memory.permanent_work_mem.size}')
+
+
 if __name__ == '__main__':
     XMem, InferenceCore, MemoryManager, mu = ref_modules()
+    if len(sys.argv) > 1 and sys.argv[1] == 'chair':
+        golden_chair(XMem, InferenceCore)
+        sys.exit(0)
     golden_attention(mu)
     golden_network(XMem, InferenceCore)
     # one object, 5 annotated frames, long-term consolidation reached (HW=24: small so CPU is quick)

@@ -91,3 +91,25 @@ def test_clip_one_object_trace_matches_reference():
 
 def test_clip_two_objects_two_groups_trace_matches_reference():
     _run_clip('two_obj')
+
+
+def test_chair_example_clip_through_the_reference_reader():
+    # BASELINE.json config 1: example_videos/chair via the reference's own VideoReader (size=160), frame 0 annotated and
+    # preloaded, 8 frames; fixture = reference outputs on CPU (tests/golden/make_golden.py chair)
+    d = np.load(os.path.join(G, 'clip_chair.npz'))
+    cfg = dict(mem_every=int(d['mem_every']), deep_update_every=-1, enable_long_term=True, enable_long_term_count_usage=True,
+               hidden_dim=64, key_dim=64, value_dim=512, top_k=30, max_mid_term_frames=10, min_mid_term_frames=5,
+               num_prototypes=128, max_long_term_elements=10000)
+    core = O.OracleCore(O.OracleNet(synth_state_dict(0)), cfg)
+    labels = [int(x) for x in d['labels']]
+    rgb = _t(d['rgb']).float()
+    msk = _t(d['mask0']).float()
+    core.set_all_labels(labels)
+    core.put_to_permanent_memory(rgb[0], msk.clone())
+    n = rgb.shape[0]
+    for ti in range(n):
+        m = msk.clone() if ti == 0 else None
+        p = core.step(rgb[ti], m, labels if m is not None else None, end=(ti == n - 1), do_not_add_mask_to_memory=m is not None)
+        ref = _t(d['probs'][ti]).float()
+        assert (p - ref).abs().mean().item() < 5e-4 and (p.argmax(0) == ref.argmax(0)).float().mean().item() > 0.999
+    assert core.mem.temp.size == int(d['temp_size']) and core.mem.perm.size == int(d['perm_size'])
