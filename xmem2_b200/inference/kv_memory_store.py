@@ -266,6 +266,10 @@ class KeyValueMemoryStore:
         survived = usage > values[-1]
         if self.num_groups > 1:
             raise NotImplementedError('The current data structure does not support feature removal with multiple object groups')
+        self.keep_columns(survived)
+
+    def keep_columns(self, survived):
+        """in-place compaction to the columns where the boolean mask `survived` [size] is set (single value group)."""
         idx = torch.nonzero(survived).flatten()
         m = idx.numel()
         self._kp[:m] = self._kp[idx]; self._s[:m] = self._s[idx]; self._e[:m] = self._e[idx]
