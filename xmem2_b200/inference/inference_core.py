@@ -48,7 +48,9 @@ class InferenceCore:
         self.all_labels = None
         # steady-state frames (no mask, not a memory frame) are replayed from a CUDA graph: ~90 kernel launches per
         # frame would otherwise be bound by host launch latency, not by the GPU.  `use_cuda_graph=False` disables it.
-        self.use_cuda_graph = config.get('use_cuda_graph', True)
+        # `t_shard=True` (extension): the memory of this ONE video is sharded over the ranks of
+        # config['t_shard_group'] (default: the world); every rank runs the same frames.  Collectives -> no graph replay.
+        self.use_cuda_graph = config.get('use_cuda_graph', True) and not config.get('t_shard', False)
         self._graphs = {}
         self._graph_warm = set()
         self._g_out = None
@@ -62,7 +64,13 @@ class InferenceCore:
         self.last_mem_ti = 0
         if not self.deep_update_sync:
             self.last_deep_update_ti = -self.deep_update_every
-        self.memory = self.memory.copy_perm_mem_only() if keep_permanent else MemoryManager(config=self.config)
+        if self.config.get('t_shard', False):
+            if keep_permanent:
+                raise NotImplementedError('keep_permanent with a T-sharded memory')
+            from .sharded_memory import ShardedMemoryManager
+            self.memory = ShardedMemoryManager(self.config, group=self.config.get('t_shard_group'))
+        else:
+            self.memory = self.memory.copy_perm_mem_only() if keep_permanent else MemoryManager(config=self.config)
         self._graphs = {}
 
     def update_config(self, config):

@@ -17,9 +17,9 @@ one group, kv_memory_store.py:171-176); all working frames have the same HW.
 
 Status: host logic verified on CPU with a world-size-2 gloo group against the single-process `MemoryManager`
 (tests/test_sharded_memory_gloo.py: the union of the shards equals the single-process banks after every step).
-Not yet driven by `InferenceCore` nor run on GPUs — the sharded READ of these shards is
-`ShardedReader.read(args, out_hwc)` with `args, n_obj = self.read_args()` plus the query fields
-(tests/test_gpu_tshard.py covers that kernel path on hand-built shards).
+`InferenceCore` uses this manager when its config has `t_shard=True` (every rank then runs the same video SPMD, CUDA
+graphs off); that end-to-end combination has NOT run on GPUs yet.  The sharded READ (`match_memory` below) goes through
+`ShardedReader.read`, whose kernels + collectives are covered by tests/test_gpu_tshard.py on hand-built shards.
 """
 from __future__ import annotations
 
@@ -28,7 +28,9 @@ from typing import List
 import torch
 import torch.distributed as dist
 
+from .. import lib
 from .memory_manager import MemoryManager
+from .tshard import ShardedReader
 
 
 def _empty(t):
@@ -45,6 +47,7 @@ class ShardedMemoryManager(MemoryManager):
         self._temp_frames: List[int] = []                  # block ids of ALL working frames still stored, oldest first
         self._perm_frames: List[int] = []                  # block ids of all permanent frames
         self._long_blocks: List[List[int]] = []            # per prototype block: [owner rank, surviving columns]
+        self._reader = None
 
     # ------------------------------------------------------------------ global <-> local bookkeeping
     def _owner_of_next(self, bank: str) -> int:
@@ -208,6 +211,39 @@ class ShardedMemoryManager(MemoryManager):
             u = parts[owner][0, 0, taken[owner]:taken[owner] + cols]
             taken[owner] += cols
             blk[1] = int((u > threshold).sum())
+
+    # ------------------------------------------------------------------ read (reference memory_manager.py:61-190)
+    def match_memory(self, query_key, selection, disable_usage_updates=False):
+        """Exact global top-k softmax readout over all shards: the staged kernels on the local columns + three NCCL
+        collectives (tshard.py).  Same signature/result as `MemoryManager.match_memory`; every rank gets the full readout.
+        NOT yet run on GPUs in this form (the kernels + collectives are covered by tests/test_gpu_tshard.py on
+        hand-built shards); a rank whose shard is still empty relies on the kernels' zero-tile path."""
+        lib.require_cuda(query_key, 'query_key')
+        if selection is None:
+            raise NotImplementedError('the fused read kernel needs the selection term (enable_long_term or need_segment path)')
+        if self._reader is None:
+            self._reader = ShardedReader(self.group)
+        h, w = query_key.shape[-2:]
+        hw = h * w
+        hw_pad = (hw + 127) // 128 * 128
+        dev = query_key.device
+        a, n_obj, use_long, _ = self.refresh_plan(dev, disable_usage_updates)
+        if a.n_groups != 1:
+            raise NotImplementedError('T-sharded read supports a single object group')
+        wsb = self._ensure_ws(hw, n_obj, dev)
+        krows = query_key[0].permute(1, 2, 0).reshape(hw, -1).to(torch.float16).contiguous()
+        erows = selection[0].permute(1, 2, 0).reshape(hw, -1).to(torch.float16).contiguous()
+        qp, bsq = lib.query_pack(krows, erows, hw_pad)
+        out = torch.empty((n_obj, hw, lib.CV), dtype=torch.float16, device=dev)
+        a.qp, a.bsq, a.hw, a.hw_pad = qp.data_ptr(), bsq.data_ptr(), hw, hw_pad
+        a.workspace, a.workspace_bytes = self._ws.data_ptr(), wsb
+        a.plan_is_resident = 0                      # the staged entry points build and upload the plan themselves
+        self._reader.read(a, out)
+        if self.enable_long_term and not disable_usage_updates:
+            self.temporary_work_mem.tick_life()
+            if use_long and self.enable_long_term_usage:
+                self.long_mem.tick_life()
+        return out.view(n_obj, h, w, lib.CV).permute(0, 3, 1, 2)
 
     # ------------------------------------------------------------------ description of the local shard for the read kernels
     def read_args(self):
