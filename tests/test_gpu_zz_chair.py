@@ -17,6 +17,8 @@ G = os.path.join(os.path.dirname(__file__), 'golden')
 torch.set_grad_enabled(False)
 
 
+@pytest.mark.xfail(strict=False, reason='written after the last GPU session of round 1: bounds not yet calibrated on a B200 '
+                                        '(XPASS = fine; the CPU oracle pin of the same fixture is tests/test_oracle_golden.py)')
 def test_chair_clip_matches_reference_trace():
     dev = 'cuda'
     d = np.load(os.path.join(G, 'clip_chair.npz'))
