@@ -48,5 +48,39 @@ def build(force=False, verbose=False):
     return OUT
 
 
+EXP_OUT = os.path.join(HERE, 'libxmem2_b200_exp.so')
+EXP_SOURCES = ['conv_igemm_csk.cu', 'conv_igemm_2cta.cu', 'conv_igemm_mc.cu']
+
+
+def build_experimental(force=False):
+    """libxmem2_b200_exp.so: the round-2 head-start kernels of csrc/experimental/ (each exports one
+    `xm_conv2d_nhwc_<variant>` entry point) plus their own copy of common.cu.  NOT part of the product library and not
+    built by `build()`; `XMEM_CONV_IMPL=<variant>` makes `lib.conv2d_nhwc` call into it (see lib.py)."""
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))]
+    jobs = [(os.path.join(CSRC, 'common.cu'), os.path.join(HERE, 'build', 'exp_common.o'))]
+    jobs += [(os.path.join(CSRC, 'experimental', s), os.path.join(HERE, 'build', 'exp_' + s.replace('.cu', '.o'))) for s in EXP_SOURCES]
+    procs = []
+    for src, obj in jobs:
+        if force or _stale(obj, [src] + headers):
+            procs.append((src, subprocess.Popen([nvcc] + FLAGS + ['-c', src, '-o', obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if out.strip():
+            print(f'--- {src}\n{out}')
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError('nvcc failed (experimental)')
+    objs = [o for _, o in jobs]
+    if force or procs or _stale(EXP_OUT, objs):
+        subprocess.check_call([nvcc, '-shared', '-cudart', 'static', '-o', EXP_OUT] + objs)
+    return EXP_OUT
+
+
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    if '--experimental' in sys.argv:
+        print(build_experimental(force='--force' in sys.argv))
+    else:
+        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
