@@ -45,3 +45,27 @@ def test_chair_clip_matches_reference_trace():
     assert core.memory.temporary_work_mem.size == int(d['temp_size'])
     assert core.memory.permanent_work_mem.size == int(d['perm_size'])
     assert worst_mean < 2e-2 and worst_agree > 0.9, (worst_mean, worst_agree)
+
+
+def test_returned_probabilities_survive_later_frames():
+    """step() hands out fresh tensors like the reference (inference_core.py:152): frames replayed from a recorded graph
+    must not overwrite what an earlier call returned."""
+    from xmem2_b200.util.synth import synth_frame, synth_mask
+    dev = 'cuda'
+    cfg = dict(mem_every=3, deep_update_every=-1, enable_long_term=True, enable_long_term_count_usage=True, hidden_dim=64,
+               key_dim=64, value_dim=512, top_k=30, max_mid_term_frames=10, min_mid_term_frames=5, num_prototypes=128,
+               max_long_term_elements=10000)
+    net = XMem(dict(cfg), None).to(dev).eval()
+    net.load_weights(synth_state_dict(0))
+    core = InferenceCore(net, cfg)
+    core.set_all_labels([1])
+    H, W = 96, 128
+    kept = []
+    for ti in range(9):
+        m = synth_mask(ti, H, W, 1, [0]).to(dev) if ti == 0 else None
+        p = core.step(synth_frame(ti, H, W, structured=True).to(dev), m, [1] if m is not None else None)
+        kept.append((p, p.clone()))
+    torch.cuda.synchronize()
+    for ti, (p, snapshot) in enumerate(kept):
+        assert torch.equal(p, snapshot), ti
+    assert len({p.data_ptr() for p, _ in kept}) == len(kept)

@@ -117,7 +117,7 @@ class InferenceCore:
             if is_normal_update and not is_mem_frame:
                 prob = self._graph_step(image, mem_frame=False)
                 if prob is not None:
-                    return unpad(prob, self.pad)
+                    return unpad(prob, self.pad).clone()      # the graph's output buffer is rewritten by the next replay
             elif is_mem_frame and is_deep_update and self.deep_update_sync and not do_not_add_mask_to_memory:
                 prob = self._graph_step(image, mem_frame=True)
                 if prob is not None:
@@ -127,7 +127,7 @@ class InferenceCore:
                                            selection=self._g_out['selection'] if self.enable_long_term else None, ignore=False)
                     self.last_mem_ti = self.curr_ti
                     self.last_deep_update_ti = self.curr_ti
-                    return unpad(prob, self.pad)
+                    return unpad(prob, self.pad).clone()
 
         if (self.use_cuda_graph and mask is not None and not need_segment and is_mem_frame and not disable_memory_updates
                 and not return_key_and_stuff and image.is_cuda and mask.shape[0] == len(self.all_labels)
@@ -143,7 +143,7 @@ class InferenceCore:
                 if is_deep_update:
                     self.memory.set_hidden(g['hidden_out'].clone())
                     self.last_deep_update_ti = self.curr_ti
-                return unpad(g['pred'], self.pad)
+                return unpad(g['pred'], self.pad).clone()
 
         key, shrinkage, selection, f16, f8, f4 = self.network.encode_key(
             image, need_ek=(self.enable_long_term or need_segment), need_sk=True)
