@@ -527,3 +527,60 @@ class OracleCore:
                 self.mem.hidden = hid
                 self.last_deep_ti = self.ti
         return unpad(prob, self.pad)
+
+
+# ----------------------------------------------------------------------------------------------
+# annotation-candidate selector  (inference/frame_selection/frame_selection.py:99-244) — SURVEY.md 8f row 3,
+# the second consumer of the similarity of memory_util.py:7-39 (no softmax)
+# ----------------------------------------------------------------------------------------------
+def cycle_dissimilarity(key_a: Tensor, shr_a: Tensor, sel_a: Tensor, key_b: Tensor, shr_b: Tensor, sel_b: Tensor) -> Tensor:
+    """frame_selection.py:213-221 for one ordered pair (A = already chosen frame, B = candidate).
+    key [CK,h,w] (composite key), shr [1,h,w], sel [CK,h,w].  mean over [HW,HW] of relu(S_ab - S_ba) where
+    S_ab[n,q] = similarity(memory = A's pixel n, query = B's pixel q weighted by B's selection) and
+    S_ba[n,q] = similarity(memory = B's pixel n, query = A's pixel q weighted by A's selection)."""
+    s_ab = similarity(key_a.unsqueeze(0), shr_a.unsqueeze(0), key_b.unsqueeze(0), sel_b.unsqueeze(0))
+    s_ba = similarity(key_b.unsqueeze(0), shr_b.unsqueeze(0), key_a.unsqueeze(0), sel_a.unsqueeze(0))
+    d = (s_ab - s_ba).float()
+    return F.relu(d).sum() / d.numel()
+
+
+def composite_keys_for_selection(keys: Tensor, masks: List[Tensor], previously_chosen: List[int], alpha: float,
+                                 min_mask_presence_percent: float, epsilon: float):
+    """frame_selection.py:156-189: per-frame validity (mask covers at least `min_mask_presence_percent` PERCENT of the
+    frame, previously chosen frames are always valid) and the mask-weighted key  key*(alpha*any_object_mask + 1-alpha),
+    mask resized to the key grid with nearest-neighbour sampling."""
+    n = len(keys)
+    h, w = keys[0].shape[-2:]
+    valid, comp = [], []
+    for i in range(n):
+        m = masks[i] if masks[i].ndim == 3 else masks[i].unsqueeze(0)
+        m_bin = m.max(dim=0).values
+        ratio = (m_bin > epsilon).sum() / m_bin.numel() * 100
+        if ratio < min_mask_presence_percent and i not in previously_chosen:
+            valid.append(False); comp.append(None)
+            continue
+        small = F.interpolate(m.unsqueeze(0).float(), size=(h, w), mode='nearest')[0]
+        ck = keys[i] * small.max(dim=0, keepdim=True).values
+        ck = ck * alpha + keys[i] * (1 - alpha)
+        valid.append(True); comp.append(ck.to(keys[i].dtype))
+    return valid, comp
+
+
+def select_next_candidates(keys: Tensor, shrinkages: Tensor, selections: Tensor, masks: List[Tensor], num_next_candidates: int,
+                           previously_chosen_candidates=(0,), alpha: float = 0.5, min_mask_presence_percent: float = 0.25,
+                           only_new_candidates: bool = True, epsilon: float = 0.5) -> List[int]:
+    """frame_selection.py:99-244: greedily add the frame whose SMALLEST cycle dissimilarity to the already chosen
+    frames is the largest.  keys [N,CK,h,w], shrinkages [N,1,h,w], selections [N,CK,h,w], masks: N tensors [C,H,W]."""
+    n = len(keys)
+    chosen = list(previously_chosen_candidates)
+    valid, comp = composite_keys_for_selection(keys, masks, chosen, alpha, min_mask_presence_percent, epsilon)
+    for _ in range(num_next_candidates):
+        scores = []
+        for j in range(n):
+            if not valid[j]:
+                scores.append(torch.tensor(0.0))
+                continue
+            scores.append(min(cycle_dissimilarity(comp[c], shrinkages[c], selections[c], comp[j], shrinkages[j], selections[j])
+                              for c in chosen))
+        chosen.append(int(torch.argmax(torch.stack([torch.as_tensor(s, dtype=torch.float32) for s in scores]))))
+    return chosen[len(previously_chosen_candidates):] if only_new_candidates else chosen

@@ -203,10 +203,46 @@ def golden_chair(XMem, InferenceCore):
           f'temp={core.memory.temporary_work_mem.size} perm={core.memory.permanent_work_mem.size}')
 
 
+from tests.selector_case import selector_inputs, SELECTOR_CASES          # noqa: E402
+
+
+def golden_selector():
+    """select_next_candidates of the LIVE reference (frame_selection.py:99-244) on CPU, plus the full
+    matrix of pair scores it is built from (computed with the reference's get_similarity)."""
+    from inference.frame_selection.frame_selection import select_next_candidates as ref_select
+    from model.memory_util import get_similarity
+    import torch.nn.functional as F
+    keys, shr, sel, masks = selector_inputs()
+    picks = []
+    for c in SELECTOR_CASES:
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = ref_select(keys, shr, sel, masks, c['k'], previously_chosen_candidates=list(c['prev']), alpha=c['alpha'], device='cpu')
+        o = O.select_next_candidates(keys, shr, sel, masks, c['k'], previously_chosen_candidates=list(c['prev']), alpha=c['alpha'])
+        assert r == o, (c, r, o)
+        picks.append(r + [-1] * (8 - len(r)))
+    # pair scores at alpha = 0.5 for every ordered pair of valid frames (invalid ones: -1)
+    valid, comp = O.composite_keys_for_selection(keys, masks, [0], 0.5, 0.25, 0.5)
+    n = len(keys)
+    scores = -np.ones((n, n), dtype=np.float32)
+    for a in range(n):
+        for b in range(n):
+            if valid[a] and valid[b]:
+                s_ab = get_similarity(comp[a].unsqueeze(0), shr[a].unsqueeze(0), comp[b].unsqueeze(0), sel[b].unsqueeze(0))
+                s_ba = get_similarity(comp[b].unsqueeze(0), shr[b].unsqueeze(0), comp[a].unsqueeze(0), sel[a].unsqueeze(0))
+                d = (s_ab - s_ba).float()
+                scores[a, b] = (F.relu(d).sum() / d.numel()).item()
+                assert abs(scores[a, b] - O.cycle_dissimilarity(comp[a], shr[a], sel[a], comp[b], shr[b], sel[b]).item()) < 1e-6
+    np.savez_compressed(os.path.join(HERE, 'selector.npz'), picks=np.array(picks), valid=np.array(valid), scores=scores)
+    print('selector golden ok:', picks, 'valid', valid)
+
+
 if __name__ == '__main__':
     XMem, InferenceCore, MemoryManager, mu = ref_modules()
     if len(sys.argv) > 1 and sys.argv[1] == 'chair':
         golden_chair(XMem, InferenceCore)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'selector':
+        golden_selector()
         sys.exit(0)
     golden_attention(mu)
     golden_network(XMem, InferenceCore)

@@ -1,0 +1,47 @@
+"""Annotation-candidate selector on the GPU: `select_next_candidates` with its pair scores computed by
+the CUDA read kernel's similarity dump, against the picks and pair scores of the LIVE reference (tests/golden/selector.npz).
+Written after the last GPU session of round 1: the kernels it calls are validated (tests/test_gpu_k1.py), this composition
+has not run yet — hence the non-strict xfail and the file name that sorts last."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.selector_case import selector_inputs, SELECTOR_CASES
+from xmem2_b200.inference.frame_selection import frame_selection as fs
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), 'golden', 'selector.npz')
+UNVERIFIED = pytest.mark.xfail(strict=False, reason='written after the last GPU session of round 1; not yet run on a B200')
+
+
+@UNVERIFIED
+def test_pair_scores_match_the_reference():
+    d = np.load(G)
+    keys, shr, sel, masks = selector_inputs()
+    dev = 'cuda'
+    keys, shr, sel = keys.to(dev), shr.to(dev), sel.to(dev)
+    valid, comp = fs._composite_keys(keys, masks, [0], 0.5, 0.25, 0.5)
+    assert valid == d['valid'].tolist()
+    packed = fs._PackedFrames(comp, shr, sel, valid)
+    cands = [j for j in range(len(keys)) if valid[j]]
+    worst = 0.0
+    for a in cands:
+        got = fs._pair_scores(packed, a, cands).cpu()
+        want = torch.from_numpy(d['scores'][a, cands])
+        worst = max(worst, ((got - want).abs() / (want.abs() + 1e-2)).max().item())
+        assert got[cands.index(a)].item() == 0.0            # D(A -> A) = 0 exactly
+    # fp16 operands (keys and selections are fp16-exact in the fixture; k^2 and 2ke are rounded to fp16) vs the fp32 reference
+    assert worst < 2e-2, worst
+
+
+@UNVERIFIED
+def test_picks_match_the_reference():
+    d = np.load(G)
+    keys, shr, sel, masks = selector_inputs()
+    keys, shr, sel = keys.cuda(), shr.cuda(), sel.cuda()
+    for c, want in zip(SELECTOR_CASES, d['picks']):
+        want = [int(x) for x in want if x >= 0]
+        got = fs.select_next_candidates(keys, shr, sel, masks, c['k'], previously_chosen_candidates=list(c['prev']), alpha=c['alpha'])
+        assert got == want, (c, got, want)
