@@ -12,13 +12,15 @@ from xmem2_b200 import lib
 def test_experimental_library_builds_and_exports_its_entry_points():
     path = xb.build_experimental()
     L = C.CDLL(path)
-    for name in ('xm_conv2d_nhwc_csk', 'xm_conv2d_nhwc_2cta', 'xm_conv2d_nhwc_mc', 'xm_last_error'):
+    for name in ('xm_conv2d_nhwc_csk', 'xm_conv2d_nhwc_2cta', 'xm_conv2d_nhwc_mc', 'xm_pair_dissimilarity', 'xm_last_error'):
         assert hasattr(L, name), name
     L.xm_last_error.restype = C.c_char_p
     # argument checks run before any CUDA call
     for name in ('xm_conv2d_nhwc_csk', 'xm_conv2d_nhwc_2cta', 'xm_conv2d_nhwc_mc'):
         assert getattr(L, name)(None, None) != 0
         assert b'null args' in L.xm_last_error()
+    assert L.xm_pair_dissimilarity(None, None, None, None, 1, 54, 128, None, None, 1, None, None, None) != 0
+    assert b'null pointer' in L.xm_last_error()
 
 
 def test_switch_is_off_by_default_and_routes_only_supported_shapes(monkeypatch):
@@ -32,7 +34,7 @@ def test_switch_is_off_by_default_and_routes_only_supported_shapes(monkeypatch):
                 Fake.calls.append(name)
                 return 0
             return f
-    monkeypatch.setattr(lib, '_load_experimental', lambda: Fake())
+    monkeypatch.setattr(lib, 'load_experimental', lambda: Fake())
     monkeypatch.setattr(lib, 'stream_ptr', lambda: None)
     a = lib.XmConvArgs()
     a.cout_pad = 64

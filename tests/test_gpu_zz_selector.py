@@ -45,3 +45,22 @@ def test_picks_match_the_reference():
         want = [int(x) for x in want if x >= 0]
         got = fs.select_next_candidates(keys, shr, sel, masks, c['k'], previously_chosen_candidates=list(c['prev']), alpha=c['alpha'])
         assert got == want, (c, got, want)
+
+
+@pytest.mark.skipif(os.environ.get('XMEM_RUN_UNVERIFIED') != '1',
+                    reason='launches csrc/experimental/pair_dissim.cu, which has never run: opt in with XMEM_RUN_UNVERIFIED=1')
+def test_fused_pair_kernel_equals_the_dump_path(monkeypatch):
+    d = np.load(G)
+    keys, shr, sel, masks = selector_inputs()
+    keys, shr, sel = keys.cuda(), shr.cuda(), sel.cuda()
+    valid, comp = fs._composite_keys(keys, masks, [0], 0.5, 0.25, 0.5)
+    packed = fs._PackedFrames(comp, shr, sel, valid)
+    cands = [j for j in range(len(keys)) if valid[j]]
+    for a in cands[:4]:
+        plain = fs._pair_scores(packed, a, cands)
+        monkeypatch.setenv('XMEM_PAIR_IMPL', 'fused')
+        fused = fs._pair_scores(packed, a, cands)
+        monkeypatch.delenv('XMEM_PAIR_IMPL')
+        torch.cuda.synchronize()
+        assert torch.allclose(plain, fused, rtol=1e-4, atol=1e-6), (a, plain, fused)     # same operands, same fp32 expression
+        assert fused[cands.index(a)].item() == 0.0

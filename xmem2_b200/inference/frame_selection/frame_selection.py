@@ -17,6 +17,7 @@ A fused pair kernel (both score tiles in TMEM, relu-difference reduced in the ep
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List
 
 import numpy as np
@@ -103,8 +104,44 @@ class _PackedFrames:
         lib.check(lib.load().xm_affinity_readout(C.byref(a), lib.stream_ptr()), 'xm_affinity_readout')
 
 
+def _pair_scores_fused(packed: _PackedFrames, chosen: int, candidates: List[int]) -> torch.Tensor:
+    """Development path (XMEM_PAIR_IMPL=fused): csrc/experimental/pair_dissim.cu, one launch for all candidates; both score
+    tiles stay in TMEM.  Not validated yet — see csrc/experimental/README.md."""
+    L = lib.load_experimental()
+    dev = packed.values.device
+    if not hasattr(packed, 'stacked'):
+        ids = sorted(packed.frames)
+        slot = {f: i for i, f in enumerate(ids)}
+        hw, hwp = packed.hw, packed.hw_pad
+        kp = torch.zeros((len(ids), hwp, 2 * CK), dtype=torch.float16, device=dev)
+        qp = torch.zeros((len(ids), hwp, 2 * CK), dtype=torch.float16, device=dev)
+        bsq = torch.zeros((len(ids), hwp), dtype=torch.float32, device=dev)
+        ms = torch.zeros((len(ids), hwp), dtype=torch.float32, device=dev)
+        for f, i in slot.items():
+            fkp, fms, fqp, fbsq = packed.frames[f]
+            kp[i, :hw] = fkp[:hw]; ms[i, :hw] = fms[:hw]; qp[i] = fqp; bsq[i] = fbsq
+            bsq[i, hw:] = 0
+        packed.stacked = (slot, kp, qp, bsq, ms)
+    slot, kp, qp, bsq, ms = packed.stacked
+    tiles = packed.hw_pad // 128
+    out = torch.empty(len(candidates), dtype=torch.float32, device=dev)
+    for p0 in range(0, len(candidates), 65535):
+        part = candidates[p0:p0 + 65535]
+        pa = torch.full((len(part),), slot[chosen], dtype=torch.int32, device=dev)
+        pb = torch.tensor([slot[j] for j in part], dtype=torch.int32, device=dev)
+        partial = torch.empty((len(part), tiles * tiles), dtype=torch.float32, device=dev)
+        rc = L.xm_pair_dissimilarity(kp.data_ptr(), qp.data_ptr(), bsq.data_ptr(), ms.data_ptr(), kp.shape[0], packed.hw, packed.hw_pad,
+                                     pa.data_ptr(), pb.data_ptr(), len(part), partial.data_ptr(), out[p0:p0 + len(part)].data_ptr(),
+                                     lib.stream_ptr())
+        if rc != 0:
+            raise RuntimeError(f'xm_pair_dissimilarity failed ({rc}): {L.xm_last_error().decode()}')
+    return out
+
+
 def _pair_scores(packed: _PackedFrames, chosen: int, candidates: List[int]) -> torch.Tensor:
     """cycle dissimilarity of (A = `chosen`, B = j) for every j in `candidates` (reference :213-221) -> fp32 [len]."""
+    if os.environ.get('XMEM_PAIR_IMPL', '') == 'fused':
+        return _pair_scores_fused(packed, chosen, candidates)
     hw = packed.hw
     top_k = min(30, hw)
     s_ab, s_ba = packed.scores

@@ -189,7 +189,7 @@ _CONV_IMPL = os.environ.get('XMEM_CONV_IMPL', '')
 _exp_lib = None
 
 
-def _load_experimental() -> C.CDLL:
+def load_experimental() -> C.CDLL:
     global _exp_lib
     if _exp_lib is None:
         path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libxmem2_b200_exp.so')
@@ -199,6 +199,8 @@ def _load_experimental() -> C.CDLL:
         _exp_lib.xm_last_error.restype = C.c_char_p
         for name in ('xm_conv2d_nhwc_csk', 'xm_conv2d_nhwc_2cta', 'xm_conv2d_nhwc_mc'):
             getattr(_exp_lib, name).argtypes = [C.POINTER(XmConvArgs), C.c_void_p]
+        vp, i32 = C.c_void_p, C.c_int32
+        _exp_lib.xm_pair_dissimilarity.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, i32, vp, vp, vp]
     return _exp_lib
 
 
@@ -208,7 +210,7 @@ def _experimental_conv(a) -> bool:
         raise RuntimeError(f'XMEM_CONV_IMPL={_CONV_IMPL!r}: expected csk, 2cta or mc')
     if _CONV_IMPL in ('2cta', 'mc') and a.cout_pad % 128 != 0:
         return False                                  # pair/multicast variants need whole 128-channel tiles
-    L = _load_experimental()
+    L = load_experimental()
     rc = getattr(L, 'xm_conv2d_nhwc_' + _CONV_IMPL)(C.byref(a), stream_ptr())
     if rc != 0:
         raise RuntimeError(f'xm_conv2d_nhwc_{_CONV_IMPL} failed ({rc}): {L.xm_last_error().decode()}')
