@@ -4,6 +4,7 @@ bytes per second an SM pulls through its L2 port (ROUND1_NOTES.md: ~70 GB/s per 
 plus a fixed launch/prologue/epilogue cost.  Then predicts what the experimental variants would buy:
   csk  : cluster split-K (2-3 CTAs per output tile, DSMEM fix-up ~1.5 us) for grids that leave SMs idle
   2cta : CTA pairs, M=256, each CTA loads half of the weight tile (BN=128 or 256)
+  halo : 3x3 stride-1 layers load one haloed 36 KB input tile per 64-channel block instead of nine 16 KB boxes
 Usage: python tests/conv_model.py [GBps_per_SM] [fixed_us]"""
 import sys
 
@@ -68,8 +69,8 @@ def time_us(ctas_total, bytes_per_cta, flop_per_cta, fixup_us=0.0):
 
 
 def main():
-    tot = dict(now=0.0, csk=0.0, cta2=0.0, both=0.0)
-    print(f'{"layer":24s} {"grid":>14s} {"now":>7s} {"csk":>7s} {"2cta":>7s}   (us per launch; R={R} GB/s/SM, T0={T0} us)')
+    tot = dict(now=0.0, csk=0.0, cta2=0.0, both=0.0, halo=0.0, all=0.0)
+    print(f'{"layer":24s} {"grid":>14s} {"now":>7s} {"csk":>7s} {"2cta":>7s} {"halo":>7s}   (us per launch; R={R} GB/s/SM, T0={T0} us)')
     for name, H, W, cin, cout, k, s, cnt in SHAPES:
         Ho, Wo = H // s, W // s
         p = plan(Ho, Wo, cin, cout, k)
@@ -92,11 +93,21 @@ def main():
             cta2 = time_us(ctas2, p['ksteps'] * (16384 + bn2 * 64), p['ksteps'] * 2.0 * 128 * bn2 * 64)
         else:
             cta2 = now
+        # haloed tile: 8x16 output tiles, per 64-channel block 36 KB of input + 9 weight tiles
+        if k == 3 and s == 1:
+            tiles_h = -(-Wo // 8) * -(-Ho // 16)
+            bn_h = 128 if (p['cout_pad'] % 128 == 0 and tiles_h * (p['cout_pad'] // 128) * 2 > SMS) else 64
+            ctas_h = tiles_h * (p['cout_pad'] // bn_h)
+            blocks = cin // 64
+            halo = time_us(ctas_h, blocks * (36864 + 9 * bn_h * 128), blocks * 9 * 2.0 * 128 * bn_h * 64)
+        else:
+            halo = now
         best = min(now, csk, cta2)
+        tot['halo'] += min(now, halo) * cnt; tot['all'] += min(best, halo) * cnt
         tot['now'] += now * cnt; tot['csk'] += min(now, csk) * cnt; tot['cta2'] += min(now, cta2) * cnt; tot['both'] += best * cnt
         grid = f"({p['tiles']},{p['cout_pad'] // p['bn']},{p['splits']})x{p['bn']}"
-        print(f'{name:24s} {grid:>14s} {now:7.1f} {csk:7.1f} {cta2:7.1f}   x{cnt}')
-    print(f"frame sum: now {tot['now']:.0f} us | with csk {tot['csk']:.0f} | with 2cta {tot['cta2']:.0f} | best of both {tot['both']:.0f}"
+        print(f'{name:24s} {grid:>14s} {now:7.1f} {csk:7.1f} {cta2:7.1f} {halo:7.1f}   x{cnt}')
+    print(f"frame sum: now {tot['now']:.0f} us | with csk {tot['csk']:.0f} | with 2cta {tot['cta2']:.0f} | best of both {tot['both']:.0f} | with halo {tot['halo']:.0f} | best of all {tot['all']:.0f}"
           f"   (measured in round 1: 909 us graph-timed)")
 
 

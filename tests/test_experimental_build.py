@@ -12,11 +12,12 @@ from xmem2_b200 import lib
 def test_experimental_library_builds_and_exports_its_entry_points():
     path = xb.build_experimental()
     L = C.CDLL(path)
-    for name in ('xm_conv2d_nhwc_csk', 'xm_conv2d_nhwc_2cta', 'xm_conv2d_nhwc_mc', 'xm_pair_dissimilarity', 'xm_last_error'):
+    for name in ('xm_conv2d_nhwc_csk', 'xm_conv2d_nhwc_2cta', 'xm_conv2d_nhwc_mc', 'xm_conv2d_nhwc_halo', 'xm_pair_dissimilarity',
+                 'xm_last_error'):
         assert hasattr(L, name), name
     L.xm_last_error.restype = C.c_char_p
     # argument checks run before any CUDA call
-    for name in ('xm_conv2d_nhwc_csk', 'xm_conv2d_nhwc_2cta', 'xm_conv2d_nhwc_mc'):
+    for name in ('xm_conv2d_nhwc_csk', 'xm_conv2d_nhwc_2cta', 'xm_conv2d_nhwc_mc', 'xm_conv2d_nhwc_halo'):
         assert getattr(L, name)(None, None) != 0
         assert b'null args' in L.xm_last_error()
     assert L.xm_pair_dissimilarity(None, None, None, None, 1, 54, 128, None, None, 1, None, None, None) != 0
@@ -45,6 +46,11 @@ def test_switch_is_off_by_default_and_routes_only_supported_shapes(monkeypatch):
     monkeypatch.setattr(lib, '_CONV_IMPL', 'csk')
     a.cout_pad = 64
     assert lib._experimental_conv(a) is True and Fake.calls[-1] == 'xm_conv2d_nhwc_csk'
+    monkeypatch.setattr(lib, '_CONV_IMPL', 'halo')
+    a.ksize, a.stride = 1, 1
+    assert lib._experimental_conv(a) is False        # 1x1 layers stay on the product kernel
+    a.ksize = 3
+    assert lib._experimental_conv(a) is True and Fake.calls[-1] == 'xm_conv2d_nhwc_halo'
     monkeypatch.setattr(lib, '_CONV_IMPL', 'typo')
     with pytest.raises(RuntimeError, match='expected csk'):
         lib._experimental_conv(a)

@@ -49,11 +49,11 @@ def build(force=False, verbose=False):
 
 
 EXP_OUT = os.path.join(HERE, 'libxmem2_b200_exp.so')
-EXP_SOURCES = ['conv_igemm_csk.cu', 'conv_igemm_2cta.cu', 'conv_igemm_mc.cu', 'pair_dissim.cu']
+EXP_SOURCES = ['conv_igemm_csk.cu', 'conv_igemm_2cta.cu', 'conv_igemm_mc.cu', 'conv_igemm_halo.cu', 'pair_dissim.cu']
 
 
 def build_experimental(force=False):
-    """libxmem2_b200_exp.so: the round-2 head-start kernels of csrc/experimental/ (three `xm_conv2d_nhwc_<variant>` entry points and
+    """libxmem2_b200_exp.so: the round-2 head-start kernels of csrc/experimental/ (four `xm_conv2d_nhwc_<variant>` entry points and
     `xm_pair_dissimilarity`) plus their own copy of common.cu.  NOT part of the product library and not
     built by `build()`; `XMEM_CONV_IMPL=<variant>` makes `lib.conv2d_nhwc` call into it (see lib.py)."""
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
