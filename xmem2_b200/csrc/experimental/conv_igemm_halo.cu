@@ -11,6 +11,9 @@
 // descriptor's base_offset field (bits 49-51) = kw tells the tensor core the phase TMA used when it wrote the rows.
 // L2->SM bytes per 64-channel block: 36 KB + 9 * BN * 128 B   instead of   9 * (16 KB + BN * 128 B):
 //     BN = 64 : 108 KB vs 216 KB (2.0x less)      BN = 128 : 180 KB vs 288 KB (1.6x less)
+// Fallback layout (XMEM_HALO_3BOX=1, template THREE_BOX): three 8-pixel-wide boxes per channel block, one per kw (x0-1+kw ..), 18 KB each
+// = 54 KB; every tap view then starts on a 1024-byte boundary (kh * 1024) with the canonical SBO of 1024 B and base_offset 0 — only
+// descriptor forms the production kernels already use — at 1.5x the input bytes of the single haloed tile (still 2.7x fewer than today).
 // Pipeline: the halo tile is double buffered per channel block (afull/aempty), the nine weight tiles of a block stream
 // through their own ring (bfull/bempty).  Everything else (concatenated sources, epilogue, TMA store) is the production
 // code with the tile rectangle fixed to 8 x 16.  Only ksize 3 / stride 1; no split-K.
@@ -48,6 +51,8 @@ namespace {
 constexpr int HALO_W = 16;                       // pixel pitch of the haloed tile (x0-1 .. x0+14)
 constexpr int HALO_H = 18;                       // rows y0-1 .. y0+16
 constexpr int HALO_BYTES = HALO_H * HALO_W * 128;   // 36 KB per 64-channel block (a multiple of 1024)
+constexpr int BOX3_BYTES = HALO_H * 8 * 128;        // 18 KB: one of the three 8-pixel-wide boxes of the fallback layout
+constexpr int A_BYTES = 3 * BOX3_BYTES;             // stage size that fits both layouts (54 KB)
 constexpr int A_STAGES = 2;
 
 // K-major SWIZZLE_128B operand whose 8-row groups are `sbo_bytes` apart and whose first row sits `row_phase` rows into
@@ -92,7 +97,7 @@ struct ConvP {
 
 template <int BN, int CONV_STAGES>
 struct ConvSmem {
-    alignas(1024) uint8_t a[A_STAGES][HALO_BYTES];      // haloed input tile of one 64-channel block, double buffered
+    alignas(1024) uint8_t a[A_STAGES][A_BYTES];         // haloed input tile (36 KB) or three kw boxes (54 KB) of one 64-channel block
     alignas(1024) uint8_t b[CONV_STAGES][BN * 128];     // weight tiles (one per tap), ring
     alignas(8) uint64_t afull[A_STAGES];
     uint64_t aempty[A_STAGES];
@@ -104,7 +109,7 @@ struct ConvSmem {
     float bias[BN];
 };
 
-template <int BN, int CONV_STAGES>
+template <int BN, int CONV_STAGES, bool THREE_BOX>
 __global__ void __launch_bounds__(192)
 conv_igemm_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
     extern __shared__ uint8_t smem_raw[];
@@ -156,9 +161,15 @@ conv_igemm_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
                 const int bb = p.bcast[s] ? 0 : b;
                 const int ast = cbg % A_STAGES, aph = (cbg / A_STAGES) & 1;
                 mbar_wait(&sm.aempty[ast], aph ^ 1, 25);
-                mbar_expect_tx(&sm.afull[ast], HALO_BYTES);
                 // rows y0-1.., columns x0-1..: out-of-range pixels are zero-filled = the convolution padding
-                tma_load_4d(sm.a[ast], &maps.a[s], &sm.afull[ast], cb * 64, x0 - 1, y0 - 1, bb);
+                if (THREE_BOX) {
+                    mbar_expect_tx(&sm.afull[ast], 3 * BOX3_BYTES);
+                    for (int kw = 0; kw < 3; ++kw)
+                        tma_load_4d(sm.a[ast] + kw * BOX3_BYTES, &maps.a[s], &sm.afull[ast], cb * 64, x0 - 1 + kw, y0 - 1, bb);
+                } else {
+                    mbar_expect_tx(&sm.afull[ast], HALO_BYTES);
+                    tma_load_4d(sm.a[ast], &maps.a[s], &sm.afull[ast], cb * 64, x0 - 1, y0 - 1, bb);
+                }
                 for (int tap = 0; tap < 9; ++tap, ++it) {
                     const int st = it % CONV_STAGES, ph = (it / CONV_STAGES) & 1;
                     mbar_wait(&sm.empty[st], ph ^ 1, 21);
@@ -179,10 +190,11 @@ conv_igemm_halo_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
                     const int kh = tap / 3, kw = tap - 3 * kh;
                     mbar_wait(&sm.full[st], ph, 22);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(sm.a[ast]) + (uint32_t)((kh * HALO_W + kw) * 128);
+                    const uint32_t a0 = THREE_BOX ? smem_u32(sm.a[ast]) + (uint32_t)(kw * BOX3_BYTES + kh * 1024)
+                                                  : smem_u32(sm.a[ast]) + (uint32_t)((kh * HALO_W + kw) * 128);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        uint64_t ad = make_desc_sw128_view(a0 + j * 32, HALO_W * 128, (uint32_t)kw);
+                        uint64_t ad = THREE_BOX ? make_desc_sw128(a0 + j * 32) : make_desc_sw128_view(a0 + j * 32, HALO_W * 128, (uint32_t)kw);
                         uint64_t bd = make_desc_sw128(smem_u32(sm.b[st]) + j * 32);
                         mma_f16_ss(tmem, ad, bd, idesc, (it | j) ? 1u : 0u);
                     }
@@ -339,19 +351,19 @@ teardown:
     if (warp == 1) tmem_dealloc(tmem, BN);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool THREE_BOX>
 int launch_conv(const ConvMaps& maps, const ConvP& p, int cout_pad, cudaStream_t stream) {
     tc5_debug_init();
-    static bool attr_done = false;
+    static bool attr_done = false;          // one per template instantiation
     const int smem = (int)sizeof(ConvSmem<BN, STAGES>) + 1024;
     if (!attr_done) {
-        XM_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_halo_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        XM_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_halo_kernel<BN, STAGES, THREE_BOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
     // epilogue staging: BN/64 output boxes at the start of the halo buffers, BN/64 residual boxes at the start of the weight ring
-    static_assert(A_STAGES * HALO_BYTES >= (BN / 64) * 128 * 128 && STAGES * BN * 128 >= (BN / 64) * 128 * 128, "rings too small for the epilogue boxes");
+    static_assert(A_STAGES * A_BYTES >= (BN / 64) * 128 * 128 && STAGES * BN * 128 >= (BN / 64) * 128 * 128, "rings too small for the epilogue boxes");
     dim3 grid(p.tiles_x * p.tiles_y * p.batch, cout_pad / BN, 1);
-    XM_CHECK_CUDA(tc5_launch(conv_igemm_halo_kernel<BN, STAGES>, grid, dim3(192), smem, stream, maps, p));
+    XM_CHECK_CUDA(tc5_launch(conv_igemm_halo_kernel<BN, STAGES, THREE_BOX>, grid, dim3(192), smem, stream, maps, p));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
@@ -392,6 +404,8 @@ extern "C" int xm_conv2d_nhwc_halo(const xm_conv_args_t* a, void* stream_) {
     p.residual = (const __half*)a->residual; p.residual_bcast = a->residual_broadcast; p.residual_stride = a->cout;
     p.out = (__half*)a->out; p.out_relu = (__half*)a->out_relu; p.out_stride = a->out_stride; p.out_offset = a->out_offset;
 
+    static int three_box = -1;
+    if (three_box < 0) { const char* e = getenv("XMEM_HALO_3BOX"); three_box = (e && e[0] == '1') ? 1 : 0; }
     ConvMaps maps;
     for (int s = 0; s < 3; ++s) {
         const int ss = s < a->n_src ? s : 0;
@@ -399,7 +413,7 @@ extern "C" int xm_conv2d_nhwc_halo(const xm_conv_args_t* a, void* stream_) {
         const uint64_t nb = a->src[ss].broadcast ? 1 : a->batch;
         uint64_t d[4] = {C, (uint64_t)a->W, (uint64_t)a->H, nb};
         uint64_t st[3] = {C * 2, (uint64_t)a->W * C * 2, (uint64_t)a->H * a->W * C * 2};
-        uint32_t bx[4] = {64, (uint32_t)HALO_W, (uint32_t)HALO_H, 1};          // the haloed tile, 36 KB
+        uint32_t bx[4] = {64, (uint32_t)(three_box ? 8 : HALO_W), (uint32_t)HALO_H, 1};          // haloed tile (36 KB) or one kw box (18 KB)
         if (xm_make_tmap_f16(&maps.a[s], a->src[ss].ptr, 4, d, st, bx)) return XM_ERR_CUDA;
     }
     // debug/tuning override: XMEM_CONV_FORCE="bn,splits,stages" (0 = keep the heuristic)
@@ -444,6 +458,10 @@ extern "C" int xm_conv2d_nhwc_halo(const xm_conv_args_t* a, void* stream_) {
     }
     // weight ring: 8 KB (BN=64) / 16 KB (BN=128) tiles; 8 / 6 deep keeps ~64-96 KB of weights in flight next to the two halo buffers
     (void)f_split; (void)f_depth;
-    if (BN == 128) return launch_conv<128, 6>(maps, p, a->cout_pad, stream);
-    return launch_conv<64, 8>(maps, p, a->cout_pad, stream);
+    if (three_box) {
+        if (BN == 128) return launch_conv<128, 6, true>(maps, p, a->cout_pad, stream);
+        return launch_conv<64, 8, true>(maps, p, a->cout_pad, stream);
+    }
+    if (BN == 128) return launch_conv<128, 6, false>(maps, p, a->cout_pad, stream);
+    return launch_conv<64, 8, false>(maps, p, a->cout_pad, stream);
 }
