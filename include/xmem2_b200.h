@@ -13,6 +13,7 @@
  *                              model/group_modules.py:29-54
  *   xm_* element-wise ops      model/modules.py:63-74,88-99,135-138,166-170,236-247, model/cbam.py:23-77,
  *                              model/group_modules.py:15-26, model/aggregate.py:6-16
+ *   xm_resize_argmax           inference/run_on_video.py:165-173 (_post_process), inference/data/mask_mapper.py:56-64
  */
 #ifndef XMEM2_B200_H
 #define XMEM2_B200_H
@@ -163,6 +164,14 @@ int xm_gru(const void* values, const float* h, int64_t npix, int32_t hidden_dim,
 int xm_upsample4x_aggregate(const void* logits4, int32_t n, int32_t h4, int32_t w4, float* prob, float* logits, void* stream);
 /* value fp16 [n_obj][hw][512] (NHWC) -> arena fp16 [n_obj][512][cap] columns [col0, col0+hw)               */
 int xm_value_append(const void* value_hwc, int32_t n_obj, int32_t hw, void* arena, int64_t cap, int32_t col0, void* stream);
+
+/* ---------------------------------------------------------------- driver-side post-processing */
+/* prob fp32 [channels][in_h][in_w] with element strides (stride_c, stride_h, 1) -> out uint8 [out_h][out_w]:
+ * bilinear resize (align_corners = False) + argmax over channels (first maximum) + optional 256-entry label table.
+ * Replaces `_post_process` (inference/run_on_video.py:165-173) and MaskMapper.remap_index_mask
+ * (inference/data/mask_mapper.py:56-64) in one pass. */
+int xm_resize_argmax(const float* prob, int32_t channels, int32_t in_h, int32_t in_w, int64_t stride_c, int64_t stride_h,
+                     int32_t out_h, int32_t out_w, const uint8_t* lut, uint8_t* out, void* stream);
 
 #ifdef __cplusplus
 }

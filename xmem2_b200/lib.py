@@ -93,6 +93,7 @@ def load() -> C.CDLL:
         lib.xm_gru.argtypes = [vp, vp, i64, i32, vp, vp, vp]
         lib.xm_conv3x3_c1.argtypes = [vp, vp, f32, i32, i32, i32, i32, vp, vp]
         lib.xm_upsample4x_aggregate.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+        lib.xm_resize_argmax.argtypes = [vp, i32, i32, i32, i64, i64, i32, i32, vp, vp, vp]
         lib.xm_value_append.argtypes = [vp, i32, i32, vp, i64, i32, vp]
         _lib = lib
     return _lib
