@@ -158,7 +158,8 @@ def run_clip(XMem, InferenceCore, name, H, W, n_frames, n_obj, annotated, first_
                         order=np.array(order), annotated=np.array(sorted(annotated)), hw=np.array([H, W, n_frames, n_obj, save_every]),
                         first_frame_of=np.array(first_frame_of if first_frame_of else [0] * n_obj),
                         final_hidden=hid.numpy().astype(np.float16),
-                        temp_usage=(core.memory.temporary_work_mem.get_usage().numpy() if core.memory.temporary_work_mem.size else np.zeros(0)),
+                        temp_usage=(core.memory.temporary_work_mem.get_usage().numpy()
+                                    if (core.memory.temporary_work_mem.size and core.memory.enable_long_term) else np.zeros(0)),
                         cfg_keys=np.array(list(cfg_over.keys())), cfg_vals=np.array(list(cfg_over.values())))
     print(f'clip {name}: oracle-vs-reference max prob err {maxerr:.2e} mean {meanerr:.2e}; final sizes {sizes[-1]}')
 
@@ -240,6 +241,13 @@ if __name__ == '__main__':
     XMem, InferenceCore, MemoryManager, mu = ref_modules()
     if len(sys.argv) > 1 and sys.argv[1] == 'chair':
         golden_chair(XMem, InferenceCore)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'plain':
+        # free-running deep updates (deep_update_every > 0: not synchronised with the memory frames), two annotated frames.
+        # (enable_long_term=False cannot be pinned: the reference itself raises in add_memory, memory_manager.py:261,
+        # `selection[..., 0:0]` with selection None, as soon as permanent memory is in use.)
+        run_clip(XMem, InferenceCore, 'plain', 64, 96, 24, 1, [0, 12], None,
+                 dict(mem_every=2, deep_update_every=3, max_mid_term_frames=6, min_mid_term_frames=3, num_prototypes=16), save_every=2)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'selector':
         golden_selector()

@@ -69,3 +69,13 @@ def test_returned_probabilities_survive_later_frames():
     for ti, (p, snapshot) in enumerate(kept):
         assert torch.equal(p, snapshot), ti
     assert len({p.data_ptr() for p, _ in kept}) == len(kept)
+
+
+@pytest.mark.xfail(strict=False, reason='fixture added after the last GPU session of round 1; not yet run on a B200')
+def test_free_running_deep_updates_clip_matches_reference():
+    """deep_update_every = 3 (reference inference_core.py:84-87: deep updates not synchronised with the memory frames; every
+    frame runs eagerly except the ordinary ones) against tests/golden/clip_plain.npz, same bounds as the other clips."""
+    from tests.test_gpu_clip import _run
+    net = XMem({}, None).to('cuda').eval()
+    net.load_weights(synth_state_dict(0))
+    _run(net, 'plain')

@@ -93,6 +93,10 @@ def test_clip_two_objects_two_groups_trace_matches_reference():
     _run_clip('two_obj')
 
 
+def test_clip_free_running_deep_updates_trace_matches_reference():
+    _run_clip('plain')         # deep_update_every = 3 (not synchronised with the memory frames), two annotated frames
+
+
 def test_chair_example_clip_through_the_reference_reader():
     # BASELINE.json config 1: example_videos/chair via the reference's own VideoReader (size=160), frame 0 annotated and
     # preloaded, 8 frames; fixture = reference outputs on CPU (tests/golden/make_golden.py chair)
