@@ -27,9 +27,27 @@ def make_case(hw, sizes, n_obj, group_begins, seed=0, device='cuda', key_scale=0
     return dict(hw=hw, banks=banks, n_obj=n_obj, groups=group_begins, qk=qk, qe=qe, device=device)
 
 
-def expected(case, top_k=30):
-    """fp64 evaluation of memory_util.py:7-65 on the fp16-rounded operands the kernel consumes."""
-    qk, qe = case['qk'].double(), case['qe'].double()
+def case_from_attention_golden(device='cuda'):
+    """tests/golden/attention.npz (inputs + outputs of the LIVE reference's get_similarity / do_softmax / readout,
+    tests/golden/make_golden.py:68-88) as a kernel case: operands rounded to fp16, the fixture's 32 value channels
+    embedded in the kernel's 512 (the rest zero), its two value planes as two objects of one group."""
+    import os
+    import numpy as np
+    d = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'attention.npz'))
+    n, hw = d['mk'].shape[2], d['qk'].shape[2]
+    cap = (n + 64 + 7) // 8 * 8
+    val = torch.zeros(2, CV, cap).half()
+    val[:, :d['v'].shape[1], :n] = torch.from_numpy(d['v']).half()
+    bank = dict(key=torch.from_numpy(d['mk'][0]).t().contiguous().half(), shr=torch.from_numpy(d['ms'][0, 0]).float(), val=val, cap=cap, n=n)
+    return dict(hw=hw, banks=[None, None, bank], n_obj=2, groups=[(0, 2, [0, 0, 0])],
+                qk=torch.from_numpy(d['qk'][0]).t().contiguous().half(), qe=torch.from_numpy(d['qe'][0]).t().contiguous().half(),
+                device=device)
+
+
+def kernel_operand_similarity(case):
+    """fp64 evaluation of get_similarity (memory_util.py:7-39) on the operands as the kernel (and the reference under
+    autocast) rounds them: k^2 and 2*k*e are fp16 values, b_sq is fp32.  One [n, hw] matrix per bank (None = empty)."""
+    qe = case['qe'].double()
     keh = (case['qk'] * case['qe'])          # fp16 product like the kernel / autocast
     two_ke = (keh + keh).double()
     bsq = (case['qe'].float() * case['qk'].float() ** 2).sum(1).double()
@@ -40,8 +58,29 @@ def expected(case, top_k=30):
         k = b['key']
         k2 = (k.float() ** 2).half().double()
         sp = -(k2 @ qe.t()) + k.double() @ two_ke.t()            # [n, hw]
-        s = (sp - bsq[None, :]) * b['shr'].double()[:, None] / 8.0
-        sims.append(s)
+        sims.append((sp - bsq[None, :]) * b['shr'].double()[:, None] / 8.0)
+    return sims
+
+
+def oracle_similarity(case):
+    """oracle.similarity (the pinned restatement of memory_util.py:7-39) in fp64 on the same fp16-valued keys: differs
+    from `kernel_operand_similarity` only by the fp16 rounding of k^2 and 2*k*e (tests/test_k1_ref_vs_oracle.py)."""
+    from oracle import xmem_oracle as O
+    qk = case['qk'].double().t().unsqueeze(0); qe = case['qe'].double().t().unsqueeze(0)
+    out = []
+    for b in case['banks']:
+        if b is None:
+            out.append(None); continue
+        out.append(O.similarity(b['key'].double().t().unsqueeze(0), b['shr'].double().view(1, 1, -1), qk, qe)[0])
+    return out
+
+
+def expected(case, top_k=30):
+    """Expected readout / usage: similarity on the kernel's fp16 operands (above), then the ORACLE's do_softmax
+    (oracle.softmax_topk = memory_util.py:41-65) and the reference's `v @ affinity` with the affinity cast to fp16
+    (memory_manager.py:57-59 under autocast)."""
+    from oracle import xmem_oracle as O
+    sims = kernel_operand_similarity(case)
     outs, usages, ambiguous = [], None, torch.zeros(case['hw'], dtype=torch.bool)
     for gi, (ob, no, begins) in enumerate(case['groups']):
         cols, vals = [], []
@@ -52,15 +91,14 @@ def expected(case, top_k=30):
             vals.append(b['val'][ob:ob + no, :, begins[bi]:b['n']].double())
         s = torch.cat(cols, 0)                                    # [Ng, hw]
         v = torch.cat(vals, 2)                                    # [no, CV, Ng]
-        tv, ti = torch.topk(s, min(top_k + 1, s.shape[0]), dim=0)
         if s.shape[0] > top_k:
+            tv = torch.topk(s, top_k + 1, dim=0).values
             ambiguous |= (tv[top_k - 1] - tv[top_k]) < 3e-5
-        e = tv[:top_k].exp()
-        w = e / e.sum(0, keepdim=True)
-        aff = torch.zeros_like(s).scatter_(0, ti[:top_k], w)
+        aff, usage = O.softmax_topk(s.unsqueeze(0), top_k, want_usage=True)
+        aff = aff[0]
         outs.append(torch.einsum('ocn,nq->ocq', v, aff.half().double()))
         if gi == 0:
-            usages = aff.sum(1)
+            usages = usage[0]
             scores0 = s
     return torch.cat(outs, 0), usages, ambiguous, scores0
 

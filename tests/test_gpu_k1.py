@@ -91,3 +91,25 @@ def test_full_size_1080p_partition_of_unity():
     assert torch.equal(out_hwc.transpose(1, 2), out_chw)
     total = sum(float(u.sum()) for u in usage_bufs if u is not None)
     assert abs(total - hw) < 1e-2 * hw
+
+
+def test_reference_golden_vectors_through_the_c_abi():
+    # tests/golden/attention.npz: inputs AND outputs of the live reference's get_similarity / do_softmax(top_k=30) / readout.
+    # (a) tight: against the oracle functions on the fp16-rounded operands; (b) against the reference's own fp32 outputs,
+    # with the bound that fp16 rounding of keys / selection / values implies (asserted for the oracle on CPU too,
+    # tests/test_k1_ref_vs_oracle.py).
+    import os
+    import numpy as np
+    case = k1_ref.case_from_attention_golden()
+    r = _check(case)
+    d = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'attention.npz'))
+    out_chw, out_hwc, usage_bufs, dbg = k1_ref.run_kernel(case, 30, want_debug=True)
+    hw = case['hw']
+    assert (dbg[:, :hw].float().cpu() - torch.from_numpy(d['sim'])[0]).abs().max().item() < 6e-2
+    _, _, amb, _ = k1_ref.expected(case, 30)
+    got = out_chw.float().cpu()
+    assert (got[:, :32][:, :, ~amb] - torch.from_numpy(d['readout'])[:, :, ~amb]).abs().max().item() < 8e-2
+    assert got[:, 32:].abs().max().item() == 0.0
+    u = usage_bufs[2][:case['banks'][2]['n']].float().cpu()
+    du = (u - torch.from_numpy(d['usage'])[0]).abs()
+    assert du.mean().item() < 2e-3 and abs(u.sum().item() - hw) < 1e-2 * hw, (du.mean().item(), u.sum().item())

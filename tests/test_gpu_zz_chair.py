@@ -17,8 +17,6 @@ G = os.path.join(os.path.dirname(__file__), 'golden')
 torch.set_grad_enabled(False)
 
 
-@pytest.mark.xfail(strict=False, reason='written after the last GPU session of round 1: bounds not yet calibrated on a B200 '
-                                        '(XPASS = fine; the CPU oracle pin of the same fixture is tests/test_oracle_golden.py)')
 def test_chair_clip_matches_reference_trace():
     dev = 'cuda'
     d = np.load(os.path.join(G, 'clip_chair.npz'))
@@ -71,7 +69,6 @@ def test_returned_probabilities_survive_later_frames():
     assert len({p.data_ptr() for p, _ in kept}) == len(kept)
 
 
-@pytest.mark.xfail(strict=False, reason='fixture added after the last GPU session of round 1; not yet run on a B200')
 def test_free_running_deep_updates_clip_matches_reference():
     """deep_update_every = 3 (reference inference_core.py:84-87: deep updates not synchronised with the memory frames; every
     frame runs eagerly except the ordinary ones) against tests/golden/clip_plain.npz, same bounds as the other clips."""

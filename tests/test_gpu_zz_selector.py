@@ -13,10 +13,8 @@ from xmem2_b200.inference.frame_selection import frame_selection as fs
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), 'golden', 'selector.npz')
-UNVERIFIED = pytest.mark.xfail(strict=False, reason='written after the last GPU session of round 1; not yet run on a B200')
 
 
-@UNVERIFIED
 def test_pair_scores_match_the_reference():
     d = np.load(G)
     keys, shr, sel, masks = selector_inputs()
@@ -36,7 +34,6 @@ def test_pair_scores_match_the_reference():
     assert worst < 2e-2, worst
 
 
-@UNVERIFIED
 def test_picks_match_the_reference():
     d = np.load(G)
     keys, shr, sel, masks = selector_inputs()

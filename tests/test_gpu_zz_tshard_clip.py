@@ -12,7 +12,6 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(strict=False, reason='written after the last GPU session of round 1; not yet run on B200s')
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
 def test_two_ranks_segment_one_clip_like_the_reference():
     from tests import tshard_clip_worker

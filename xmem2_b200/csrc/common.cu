@@ -66,14 +66,27 @@ int xm_make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_
 }
 
 int xm_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev & 63;
+    if (n[slot] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n[slot] = v > 0 ? v : 148;
     }
-    return n;
+    return n[slot];
+}
+
+bool xm_first_use_on_device(XmPerDevice* token) {
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    std::lock_guard<std::mutex> lock(mu);
+    if (token->done_mask & bit) return false;
+    token->done_mask |= bit;
+    return true;
 }
 
 // ---- trap diagnostics: a host-mapped page kernels write to just before __trap() (tc5.cuh) ----
@@ -81,7 +94,7 @@ static int* g_trap_host = nullptr;
 static int* g_trap_dev = nullptr;
 int* xm_debug_trap_device_ptr() {
     if (!g_trap_host) {
-        if (cudaHostAlloc((void**)&g_trap_host, 64, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+        if (cudaHostAlloc((void**)&g_trap_host, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
         for (int i = 0; i < 16; ++i) g_trap_host[i] = 0;
         if (cudaHostGetDevicePointer((void**)&g_trap_dev, g_trap_host, 0) != cudaSuccess) return nullptr;
     }

@@ -29,6 +29,11 @@ void xm_set_error(const char* fmt, ...);
 int xm_make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box);
 
-int xm_num_sms();
+int xm_num_sms();      // SM count of the CURRENT device (cached per device ordinal)
+
+// Per-device one-time initialisation (cudaFuncSetAttribute, __device__ symbol uploads): function attributes and symbols
+// belong to a device's context, so a process that drives several GPUs has to repeat them on each one.
+struct XmPerDevice { unsigned long long done_mask; };       // zero-initialised static at the call site; <= 64 devices
+bool xm_first_use_on_device(XmPerDevice* token);             // true exactly once per (token, current device); thread-safe
 
 void xm_count_launches(int n);

@@ -354,11 +354,10 @@ teardown:
 template <int BN, int STAGES>
 int launch_conv(const ConvMaps& maps, const ConvP& p, int cout_pad, cudaStream_t stream) {
     tc5_debug_init();
-    static bool attr_done = false;
+    static XmPerDevice attr_token = {0};
     const int smem = (int)sizeof(ConvSmem<BN, STAGES>) + 1024;
-    if (!attr_done) {
+    if (xm_first_use_on_device(&attr_token)) {
         XM_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
     }
     dim3 grid(p.tiles_x * p.tiles_y * p.batch, cout_pad / BN, p.splits);
     XM_CHECK_CUDA(tc5_launch(conv_igemm_kernel<BN, STAGES>, grid, dim3(192), smem, stream, maps, p));

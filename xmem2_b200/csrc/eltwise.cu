@@ -604,10 +604,9 @@ extern "C" int xm_conv3x3_c1(const void* in, const void* weight_tap_c, float bia
     XM_REQUIRE(in && weight_tap_c && out && C == 256, "xm_conv3x3_c1: specialised for C = 256 (decoder.pred)");
     const int blocks = B * ((H + 7) / 8) * ((W + 7) / 8);
     const size_t smem = (size_t)100 * (C / 8) * 16;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static XmPerDevice attr_token = {0};
+    if (xm_first_use_on_device(&attr_token)) {
         XM_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_c1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
     }
     XM_CHECK_CUDA(tc5_launch(conv3x3_c1_kernel, dim3(blocks), dim3(256), smem, STREAM, (const __half*)in, (const __half*)weight_tap_c,
                              bias, B, H, W, C, (__half*)out));

@@ -818,12 +818,11 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
     const int qtiles = hw_pad / TQ;
 
     tc5_debug_init();
-    static bool attr_done = false;
-    if (!attr_done) {
+    static XmPerDevice attr_token = {0};
+    if (xm_first_use_on_device(&attr_token)) {
         XM_CHECK_CUDA(cudaFuncSetAttribute(k1_scan<MODE_SLOTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem) + 1024));
         XM_CHECK_CUDA(cudaFuncSetAttribute(k1_scan<MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem) + 1024));
         XM_CHECK_CUDA(cudaFuncSetAttribute(k1_readout_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2Smem) + 1024));
-        attr_done = true;
     }
 
     uint8_t* ws = (uint8_t*)a->workspace;
@@ -927,12 +926,11 @@ static int tshard_setup(const xm_affinity_args_t* a, cudaStream_t stream, Tshard
     XM_REQUIRE(a->top_k > 0 && a->top_k <= XM_MAX_TOPK && a->qp && a->bsq && a->workspace, "xm_affinity_tshard: bad arguments");
     XM_REQUIRE(a->workspace_bytes >= xm_affinity_workspace_bytes(a->hw, a->n_obj_total), "xm_affinity_tshard: workspace too small");
     tc5_debug_init();
-    static bool attr_done = false;
-    if (!attr_done) {
+    static XmPerDevice attr_token = {0};
+    if (xm_first_use_on_device(&attr_token)) {
         XM_CHECK_CUDA(cudaFuncSetAttribute(k1_scan<MODE_SLOTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem) + 1024));
         XM_CHECK_CUDA(cudaFuncSetAttribute(k1_scan<MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem) + 1024));
         XM_CHECK_CUDA(cudaFuncSetAttribute(k1_readout_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2Smem) + 1024));
-        attr_done = true;
     }
     const int hw_pad = a->hw_pad;
     uint8_t* ws = (uint8_t*)a->workspace;

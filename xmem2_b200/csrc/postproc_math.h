@@ -17,8 +17,16 @@
 // PyTorch's source index for align_corners=False (ATen UpSample.h, area_pixel_compute_source_index): the centre of
 // destination pixel `dst` mapped back, clamped at 0; i0 = floor, i1 = i0 + (i0 < in-1), lambda = fractional part.
 XM_HD void xm_bilinear_tap(int dst, int in_size, int out_size, int* i0, int* i1, float* lambda1) {
+    // exact IEEE division: the library is compiled with --use_fast_math, whose approximate division (2 ulp) moved the
+    // source coordinate of 480 -> 1080 resizes by ~1e-4 pixels (round-1 failure of tests/test_gpu_zz_postproc.py on the
+    // B200).  ATen's CUDA kernel evaluates `scale * (dst + 0.5) - 0.5` with nvcc's default FMA contraction.
+#ifdef __CUDA_ARCH__
+    const float scale = __fdiv_rn((float)in_size, (float)out_size);
+    float src = fmaf(scale, (float)dst + 0.5f, -0.5f);
+#else
     const float scale = (float)in_size / (float)out_size;
     float src = scale * ((float)dst + 0.5f) - 0.5f;
+#endif
     if (src < 0.f) src = 0.f;
     int i = (int)src;
     if (i > in_size - 1) i = in_size - 1;

@@ -200,11 +200,12 @@ static inline cudaError_t tc5_launch(void (*kernel)(KArgs...), dim3 grid, dim3 b
 
 // host: point this translation unit's trap buffer at the shared host-mapped page (common.cu)
 int* xm_debug_trap_device_ptr();
+struct XmPerDevice;
+bool xm_first_use_on_device(XmPerDevice* token);
 static inline void tc5_debug_init() {
-    static bool done = false;
-    if (!done) {
+    static unsigned long long done_mask = 0;            // layout-compatible with XmPerDevice (common.h)
+    if (xm_first_use_on_device(reinterpret_cast<XmPerDevice*>(&done_mask))) {
         int* p = xm_debug_trap_device_ptr();
         cudaMemcpyToSymbol(tc5::g_tc5_trap_buf, &p, sizeof(p));
-        done = true;
     }
 }

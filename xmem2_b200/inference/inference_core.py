@@ -170,7 +170,9 @@ class InferenceCore:
                 mask = mask.type_as(pred_prob_no_bg)
                 if valid_labels is not None:
                     unlabelled = [i for i in range(pred_prob_no_bg.shape[0]) if (i + 1) not in valid_labels]
-                    mask[unlabelled] = pred_prob_no_bg[unlabelled]
+                    if unlabelled:
+                        mask = mask.clone()      # never write into the caller's tensor (pad_divide_by / type_as may alias it)
+                        mask[unlabelled] = pred_prob_no_bg[unlabelled]
             pred_prob_with_bg = aggregate(mask, dim=0)
             if not disable_memory_updates:
                 self.memory.create_hidden_state(len(self.all_labels), key)
@@ -222,6 +224,10 @@ class InferenceCore:
             if ph is not None and ph.data_ptr() == g_hidden.data_ptr():
                 prev.memory.set_hidden(ph.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3))
         g['owner'][0] = weakref.ref(self)
+        # the recorded read kernels have the K1 workspace address (device-side plan + scratch) baked in: a core that
+        # inherits a graph recorded by an earlier core (same recycled arenas -> same signature) adopts that workspace
+        if mem._ws is not g['ws']:
+            mem.adopt_workspace(g['ws'])
         hid = mem.get_hidden()
         if hid.data_ptr() != g_hidden.data_ptr():
             g_hidden.copy_(hid)
@@ -266,6 +272,7 @@ class InferenceCore:
                 g.update(key=key, shrinkage=shrinkage, selection=selection, value=value)
             shared.copy_(hidden)
         g['graph'] = graph
+        g['ws'] = mem._ws                       # keeps the workspace the recorded kernels point into alive
         g['launches'] = int(lib.load().xm_launch_count() - launches0)     # recorded, not executed
         lib.load().xm_add_launch_count(-g['launches'])
         if os.environ.get('XMEM_TRACE'):

@@ -113,6 +113,11 @@ class MemoryManager:
             self._plan_key = None
         return wsb
 
+    def adopt_workspace(self, ws):
+        """Use `ws` (the workspace a recorded CUDA graph points into) from now on; the device-side plan is re-uploaded."""
+        self._ws = ws
+        self._plan_key = None
+
     def upload_plan(self, hw, device, disable_usage_updates=False):
         a, n_obj, use_long, key = self.refresh_plan(device, disable_usage_updates)
         wsb = self._ensure_ws(hw, n_obj, device)
