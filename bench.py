@@ -129,7 +129,7 @@ def k1_roofline(device):
         bk.cap, bk.n_obj_cap, bk.size = b['cap'], 1, b['n']
     a.n_groups = 1; a.groups[0].obj_begin, a.groups[0].n_obj = 0, 1
     qp, bsq = lib.query_pack(case['qk'].to(device).contiguous(), case['qe'].to(device).contiguous(), hw_pad)
-    wsb = L.xm_affinity_workspace_bytes(hw, 1); ws = torch.empty(wsb, dtype=torch.uint8, device=device)
+    ws = lib.affinity_workspace(hw, 1, device); wsb = ws.numel()
     out = torch.empty(1, hw, 512, dtype=torch.float16, device=device)
     a.qp, a.bsq, a.hw, a.hw_pad, a.top_k, a.n_obj_total = qp.data_ptr(), bsq.data_ptr(), hw, hw_pad, 30, 1
     a.readout_hwc, a.workspace, a.workspace_bytes = out.data_ptr(), ws.data_ptr(), wsb

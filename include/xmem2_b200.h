@@ -43,7 +43,10 @@ void xm_add_launch_count(int n);   /* the host mirror reports kernels it replays
 /* programmatic dependent launch between this library's kernels (default on) */
 void xm_set_pdl(int on);
 
-/* ---------------------------------------------------------------- memory read (K1) */
+/* ---------------------------------------------------------------- memory read (K1)
+ * xm_affinity_readout launches ONE persistent kernel per object group (one CTA per SM, all co-resident, phases separated by
+ * inter-CTA barriers on counters in the workspace): do not run two affinity calls that share a workspace concurrently, and
+ * do not share the device with another long-running kernel while it runs. */
 /* One memory bank (KeyValueMemoryStore, inference/kv_memory_store.py:4-239) as the kernel sees it. */
 typedef struct {
     const void* keys;       /* fp16 [cap][128]: row n = (k[n,:]^2 , k[n,:])  — "packed" keys           */
@@ -83,6 +86,9 @@ typedef struct {
 } xm_affinity_args_t;
 
 int64_t xm_affinity_workspace_bytes(int32_t hw, int32_t n_obj_total);
+/* A fresh workspace needs its inter-CTA barrier counters zeroed ONCE before the first xm_affinity_* launch that uses it
+ * (the kernel re-arms them on exit, so CUDA-graph replays need nothing). */
+int xm_affinity_workspace_init(void* workspace, int64_t workspace_bytes, int32_t hw, int32_t n_obj_total, void* stream);
 int xm_affinity_readout(const xm_affinity_args_t* args, void* stream);
 /* host only: validate banks/groups and write the 4096-byte column-range plan the kernels read from the head of
  * the workspace (copy it there with any stream-ordered H2D copy).  Launch shapes of xm_affinity_readout depend only

@@ -128,8 +128,8 @@ def run_kernel(case, top_k=30, want_debug=False):
         for bi in range(3):
             a.groups[gi].begin[bi] = begins[bi]
     qp, bsq = lib.query_pack(case['qk'].to(dev).contiguous(), case['qe'].to(dev).contiguous(), hw_pad)
-    wsb = L.xm_affinity_workspace_bytes(hw, case['n_obj'])
-    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ws = lib.affinity_workspace(hw, case['n_obj'], dev)
+    wsb = ws.numel()
     out_chw = torch.zeros(case['n_obj'], CV, hw, dtype=torch.float16, device=dev)
     out_hwc = torch.zeros(case['n_obj'], hw, CV, dtype=torch.float16, device=dev)
     a.qp, a.bsq, a.hw, a.hw_pad, a.top_k, a.n_obj_total = qp.data_ptr(), bsq.data_ptr(), hw, hw_pad, top_k, case['n_obj']

@@ -32,6 +32,7 @@ class Stats:
         self.eps = 0.0
         self.mean_dprob = 0.0
         self.frames = 0
+        self.per_frame = []          # (frame, argmax mismatch fraction, largest oracle margin among the mismatches)
 
     def add(self, p, po):
         d, do = _log_odds(p), _log_odds(po)
@@ -45,15 +46,19 @@ class Stats:
         am, amo = p.argmax(0), po.argmax(0)
         bad = am != amo
         self.mismatch += int(bad.sum()); self.pixels += bad.numel()
+        eps_f = 0.0
         if bad.any():
             top2 = po.float().clamp_min(1e-30).log().topk(2, dim=0).values
-            self.eps = max(self.eps, (top2[0] - top2[1])[bad].max().item())
+            eps_f = (top2[0] - top2[1])[bad].max().item()
+            self.eps = max(self.eps, eps_f)
+        self.per_frame.append((self.frames, round(float(bad.float().mean()), 6), round(eps_f, 4)))
         self.mean_dprob = max(self.mean_dprob, (p.float() - po.float()).abs().mean().item())
         self.frames += 1
 
     def as_dict(self):
         return dict(dlogit_p50=self.p50, dlogit_p99=self.p99, dlogit_max=self.max, argmax_mismatch_frac=self.mismatch / max(1, self.pixels),
-                    argmax_eps=self.eps, mean_dprob=self.mean_dprob, frames=self.frames)
+                    argmax_eps=self.eps, mean_dprob=self.mean_dprob, frames=self.frames,
+                    worst_frames=sorted(self.per_frame, key=lambda t: -t[1])[:8])
 
 
 def run_lockstep(net, state, H, W, n_frames, n_obj, annotated, first_frame_of, cfg, structured, seed=1234, with_autocast=False,

@@ -47,6 +47,8 @@ def _record(name, ours, auto):
 def _assert_bars(name, stats):
     bars, got = BARS[name], stats.as_dict()
     for k, bar in bars.items():
+        if k.startswith('_'):
+            continue
         assert got[k] <= bar, (name, k, got[k], bar, got)
 
 
@@ -62,9 +64,10 @@ def test_config2_480p_clip_matches_fp32_oracle(setup):
 
 def test_config3_portrait_two_objects_through_first_consolidation(setup):
     # 853x480 -> 54x30 grid, object 2 first appears at the second annotated frame (two value groups with suffix ranges),
-    # working memory fills at ti = 100 -> first consolidation into 128 long-term prototypes, then 11 frames read all 3 banks
+    # the annotated frames are not added to the working memory (do_not_add_mask_to_memory), so it holds 10 frames at
+    # ti = 140 -> first consolidation into 128 long-term prototypes, then 11 more frames read all three banks
     state, net = setup
-    ours, _, (core, ocore) = run_lockstep(net, state, 853, 480, 112, 2, [0, 20, 40, 60, 80], [0, 20], CFG, structured=True)
+    ours, _, (core, ocore) = run_lockstep(net, state, 853, 480, 152, 2, [0, 20, 40, 60, 80], [0, 20], CFG, structured=True)
     _record('config3_portrait_2obj', ours, None)
     assert core.memory.long_mem.size == 128 and ocore.mem.long.size == 128
     assert core.memory.permanent_work_mem.obj_groups == [[0], [1]]

@@ -60,4 +60,4 @@ def test_fused_pair_kernel_equals_the_dump_path(monkeypatch):
         monkeypatch.delenv('XMEM_PAIR_IMPL')
         torch.cuda.synchronize()
         assert torch.allclose(plain, fused, rtol=1e-4, atol=1e-6), (a, plain, fused)     # same operands, same fp32 expression
-        assert fused[cands.index(a)].item() == 0.0
+        assert abs(fused[cands.index(a)].item()) < 1e-6        # the two score tiles come from different MMA streams

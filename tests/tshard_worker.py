@@ -39,8 +39,8 @@ def build_args(case, cols, dev, top_k=30):
     bk.cap, bk.n_obj_cap, bk.size = cap, case['n_obj'], n
     a.n_groups = 1; a.groups[0].obj_begin, a.groups[0].n_obj = 0, case['n_obj']
     qp, bsq = lib.query_pack(case['qk'].to(dev).contiguous(), case['qe'].to(dev).contiguous(), hw_pad)
-    wsb = lib.load().xm_affinity_workspace_bytes(hw, case['n_obj'])
-    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ws = lib.affinity_workspace(hw, case['n_obj'], dev)
+    wsb = ws.numel()
     a.qp, a.bsq, a.hw, a.hw_pad, a.top_k, a.n_obj_total = qp.data_ptr(), bsq.data_ptr(), hw, hw_pad, top_k, case['n_obj']
     a.workspace, a.workspace_bytes = ws.data_ptr(), wsb
     return a, (rows, shr, val, usage, qp, bsq, ws)

@@ -82,7 +82,7 @@ class _PackedFrames:
         self.values = torch.zeros((1, CV, self.cap), dtype=torch.float16, device=dev)
         self.readout = torch.empty((1, self.hw, CV), dtype=torch.float16, device=dev)
         wsb = lib.load().xm_affinity_workspace_bytes(self.hw, 1)
-        self.ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        self.ws = lib.affinity_workspace(self.hw, 1, dev)
         self.scores = [torch.empty((self.hw, self.hw_pad), dtype=torch.float32, device=dev) for _ in range(2)]
 
     def similarity(self, mem: int, query: int, out: torch.Tensor, top_k: int):

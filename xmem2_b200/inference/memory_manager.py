@@ -109,7 +109,7 @@ class MemoryManager:
     def _ensure_ws(self, hw, n_obj, device):
         wsb = lib.load().xm_affinity_workspace_bytes(hw, n_obj)
         if self._ws is None or self._ws.numel() < wsb or self._ws.device != device:
-            self._ws = torch.empty(wsb, dtype=torch.uint8, device=device)
+            self._ws = lib.affinity_workspace(hw, n_obj, device)
             self._plan_key = None
         return wsb
 

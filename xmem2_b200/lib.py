@@ -74,6 +74,7 @@ def load() -> C.CDLL:
         lib.xm_version.restype = C.c_int
         lib.xm_affinity_workspace_bytes.restype = C.c_int64
         lib.xm_affinity_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+        lib.xm_affinity_workspace_init.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
         lib.xm_affinity_readout.argtypes = [C.POINTER(XmAffinityArgs), C.c_void_p]
         lib.xm_affinity_plan.argtypes = [C.POINTER(XmAffinityArgs), C.c_void_p, C.c_int64]
         lib.xm_query_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -128,6 +129,16 @@ def require_cuda(t: torch.Tensor, name: str):
 # ------------------------------------------------------------------------------------------------
 # thin typed wrappers
 # ------------------------------------------------------------------------------------------------
+def affinity_workspace(hw: int, n_obj: int, device) -> torch.Tensor:
+    """Workspace of the fused read kernel for `hw` query positions and `n_obj` value planes.  Its inter-CTA barrier counters
+    have to be zero before the first launch (the kernel re-arms them itself on exit): xm_affinity_workspace_init."""
+    wsb = load().xm_affinity_workspace_bytes(hw, n_obj)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=device)
+    with torch.cuda.device(ws.device):
+        check(load().xm_affinity_workspace_init(ws.data_ptr(), wsb, hw, n_obj, stream_ptr()), 'xm_affinity_workspace_init')
+    return ws
+
+
 def query_pack(key_hwc: torch.Tensor, sel_hwc: torch.Tensor, hw_pad: int):
     """key/sel [hw,64] fp16 contiguous -> (qp [hw_pad,128] fp16, bsq [hw_pad] fp32)."""
     require_cuda(key_hwc, 'key')
