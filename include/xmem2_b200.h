@@ -94,11 +94,18 @@ int xm_affinity_readout(const xm_affinity_args_t* args, void* stream);
  * the workspace (copy it there with any stream-ordered H2D copy).  Launch shapes of xm_affinity_readout depend only
  * on (hw, n_obj_total, group object counts), never on bank sizes.                                          */
 int xm_affinity_plan(const xm_affinity_args_t* args, void* host_plan_out, int64_t bytes);
+/* diagnostics (synchronous): globaltimer stamps [n_ctas][16] of the phase boundaries of the last launch on this workspace;
+ * returns the number of CTAs copied.  Index: 0 start, 1 sweep A done, 2/3 merge A, 4 sweep B done, 5 lists published,
+ * 6 merge B done, 7 readout start, 8 readout done, 9 reduce start, 10 end. */
+int xm_affinity_debug_timeline(void* workspace, int32_t hw, int32_t n_obj_total, unsigned long long* host_out, int32_t max_ctas);
+/* diagnostics, only meaningful when the library was built with -DK1_TRACE: per-tile clock records of CTA 0 ([4][1024] uint64) */
+int xm_affinity_debug_counts(void* workspace, int32_t hw, int32_t n_obj_total, int32_t* host_out_per_query);
+int xm_affinity_debug_trace(void* workspace, int32_t hw, int32_t n_obj_total, unsigned long long* host_out);
 
 /* T-sharded read: the banks of one long video are split over R ranks by stored frame; every rank
  * has the same query.  The host interleaves the collectives (torch.distributed / NCCL):
  *   stage_a -> all_reduce(MAX) tau_lo[hw_pad] -> stage_b -> all_gather top32[R][hw_pad][32] -> merge (every rank)
- *   -> stage_c -> all_reduce(SUM) readout_f32[n_obj][512][hw_pad] -> cast.   One object group per call (groups[0]);
+ *   -> stage_c -> all_reduce(SUM) readout_f32[n_obj][hw_pad][512] -> cast.   One object group per call (groups[0]);
  * a rank may hold fewer than top_k (even zero) columns.  Same math as xm_affinity_readout (model/memory_util.py:7-65). */
 int xm_affinity_tshard_stage_a(const xm_affinity_args_t* args, float* tau_lo_local, void* stream);
 int xm_affinity_tshard_stage_b(const xm_affinity_args_t* args, const float* tau_lo_global, float* top32_local, void* stream);

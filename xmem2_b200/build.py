@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libxmem2_b200.so')
 SOURCES = ['common.cu', 'k1_affinity.cu', 'conv_igemm.cu', 'eltwise.cu', 'postproc.cu']
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math',
-         '-Xcompiler', '-fPIC', '-cudart', 'static']
+         '-Xcompiler', '-fPIC', '-cudart', 'static'] + os.environ.get('XMEM_EXTRA_NVCC_FLAGS', '').split()
 
 
 def _stale(target, deps):

@@ -27,6 +27,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include "common.h"
 #include "tc5.cuh"
 
@@ -40,8 +41,8 @@ constexpr int TN = 128;                 // sweep: memory columns per key tile
 constexpr int TK = 64;                  // readout: memory columns per value tile ("k-tile")
 constexpr int KP = 128;                 // packed key width
 constexpr int LISTK = XM_MAX_TOPK;      // 32
-constexpr int NSLOT = 16;               // slot maxima per scan thread
-constexpr int LCAP = 64;                // candidate capacity per (column slice, query)
+constexpr int NSLOT = 8;                // slot maxima per scan thread
+constexpr int LCAP = 32;                // candidate capacity per scan thread = (column slice, tile parity, query); >= top_k keeps it exact
 constexpr int MAX_SLICE1 = 32;          // column slices per query pair in the sweeps
 constexpr int P1_KSTAGES = 4;
 constexpr int P2_VSTAGES = 3;
@@ -93,22 +94,26 @@ struct K1Params {
     int do_usage;
     int mode;
     int qtiles, qpairs, nslice1;
+    int a_stride;            // sweep A looks at every a_stride-th key tile only (any subset of real scores gives a valid lower bound)
     int n_rows, n_items;
     unsigned* ctr;
-    float* candA;            // [qpairs*256][nslice1*32]
+    float* candA;            // [qpairs*256][nslice1][2 * NSLOT]
     float* tau_lo;           // [qpairs*256]
     uint2* lists;            // [qpairs*256][nslice1][LCAP]  (score bits, linear column)
     int* lcnt;               // [qpairs*256][nslice1]
     uint2* fin;              // [qpairs*256][32]             (linear column or -1, weight bits)
     float* partial;          // [n_items][256][256]
+    unsigned long long* uacc; // [max_columns] fixed-point (2^-40) column sums of the affinity (usage), order independent
+    int uacc_cols;
     const float* tau_ext;    // MODE_EXT_TAU
     const float* inv_ext;
     float* top32_out;        // MODE_EXPORT32
-    float* out_f32;          // fp32 [n_obj][512][hw_pad] (T-shard) or null
+    float* out_f32;          // fp32 [n_obj][hw_pad][512] (T-shard) or null
     __half* out_chw;
     __half* out_hwc;
     int out_obj_total;
     float* dbg;
+    unsigned long long* timeline;   // [grid][16] globaltimer stamps of the phase boundaries (diagnostics, always written)
     uint8_t row_slices[MAX_ROWS_TABLE];
 };
 
@@ -120,20 +125,35 @@ __device__ __forceinline__ float fast_exp(float x) {
 __device__ __forceinline__ uint32_t f2ord(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __device__ __forceinline__ float ord2f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));       // FMNMX3 (sm_100+)
+    return r;
+}
 __device__ __forceinline__ float score2(uint32_t acc_bits, float bsq8, float ms) {
     // ((S' - b_sq) * shrinkage) / 8 == (S'/8 - b_sq/8) * shrinkage exactly (power-of-two scaling commutes with rounding)
     return fmaf(__uint_as_float(acc_bits), 0.125f, -bsq8) * ms;
 }
 
-__device__ __forceinline__ void tmem_ld_32x32b_x1(uint32_t taddr, uint32_t& v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
-}
 // global -> shared bulk copy (1-D TMA) completing on an mbarrier; 16-byte aligned addresses, size a multiple of 16
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_inval(uint64_t* bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return t; }
+#ifdef K1_TRACE
+// cycle accounting of CTA 0 (diagnostics build): every role accumulates clock64() differences in registers and writes its totals
+// once per sweep into the trace area behind the time stamps ([role slot][sweep][counter])
+#define K1_CLK() clock64()
+#define K1_ACC(var, t0) do { var += clock64() - (t0); } while (0)
+#define K1_TRACE_OUT(slot, sweep, c0, c1, c2) do { if (blockIdx.x == 0) { unsigned long long* tb_ = p.timeline + 148 * 16 + ((slot) * 2 + (sweep)) * 4; \
+    tb_[0] = (unsigned long long)(c0); tb_[1] = (unsigned long long)(c1); tb_[2] = (unsigned long long)(c2); } } while (0)
+#else
+#define K1_CLK() 0ll
+#define K1_ACC(var, t0) do { } while (0)
+#define K1_TRACE_OUT(slot, sweep, c0, c1, c2) do { } while (0)
+#endif
+#define K1_STAMP(i) do { if (threadIdx.x == 0) p.timeline[(size_t)blockIdx.x * 16 + (i)] = global_ns(); } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // operand packing
@@ -188,16 +208,15 @@ struct KStage {                                              // one key tile: re
 struct SweepSmem {
     alignas(1024) uint8_t q[2][2][TQ * 128];                 // [q-tile of the pair][K half] 128 rows x 128 B
     KStage st[P1_KSTAGES];                                   // merge scratch aliases this
-    int cnt[QPAIR];                                          // sweep B: entries in this CTA's list of each query
-    int lock[QPAIR];
-    float lmin[QPAIR];                                       // smallest listed score once a list is full (else -inf)
 };
 struct ReadSmem {
     alignas(1024) uint8_t v[P2_VSTAGES][256 * 128];          // [stage] 256 channel rows x (64 columns = 128 B); reduce scratch aliases this
     alignas(1024) uint8_t p[2][2][TQ * 128];                 // [buffer][q-tile] 128 query rows x (64 columns = 128 B)
-    uint32_t ent[P2_MAXENT];                                 // (q-tile << 13 | row << 6 | column) | fp16 weight << 16, sorted by k-tile
+    float entw[P2_MAXENT];                                   // weights of this item's entries, bucketed by k-tile
+    uint16_t entp[P2_MAXENT];                                // their position in the P tile: q-tile << 13 | row << 6 | column
     uint32_t cur[P2_MAXKT + 1];
     uint16_t off[P2_MAXKT + 2];
+    unsigned long long utile[2][TK];                         // per builder: fixed-point column sums of the current k-tile
 };
 struct CommonSmem {
     alignas(8) uint64_t qfull;
@@ -226,16 +245,22 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 // Barrier among the CTAs that increment `ctr` (all co-resident: one CTA per SM, grid <= #SMs).  Bounded: a protocol bug or a
 // CTA that never became resident traps instead of hanging the GPU.
-__device__ void cta_group_barrier(unsigned* ctr, unsigned target, int tag) {
+__device__ void cta_group_barrier(unsigned* ctr, unsigned target, int tag, unsigned long long* stamps = nullptr) {
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (stamps) stamps[11] = global_ns();
         __threadfence();
+        if (stamps) stamps[12] = global_ns();
         atomicAdd(ctr, 1u);
-        unsigned spins = 0;
+        if (stamps) stamps[13] = global_ns();
+        unsigned long long t0 = 0ull;
         while (ld_acquire_u32(ctr) < target) {
             __nanosleep(40);
-            if (++spins > (1u << 25)) mbar_timeout(tag, target);
+            const unsigned long long now = global_ns();
+            if (t0 == 0ull) t0 = now;
+            if (now - t0 > 4000000000ull) mbar_timeout(tag, target);      // 4 s: a CTA never arrived
         }
+        if (stamps) stamps[14] = global_ns();
         __threadfence();
     }
     __syncthreads();
@@ -260,39 +285,34 @@ __device__ __forceinline__ void unlinear_col(const K1Seg& sg, int lin, int& s, i
     col = sg.origin[s] + (lin - sg.t64[s] * TK);
 }
 
-// Append (score, column) to this CTA's list of query `ql`; when the list is full keep the LCAP largest (exact top-LCAP of the
-// slice).  The four scan threads of a query (different warps) serialise on a shared-memory lock; appends are rare (~0.2 % of
-// the scores), replace-min only in the pathological case of > 64 survivors in one slice.
-__device__ __noinline__ void list_append(float sc, int lin, int ql, SweepSmem& sm, uint2* glist, float& thr) {
-    while (atomicCAS(&sm.lock[ql], 0, 1) != 0) { }
-    __threadfence_block();
-    volatile int* cntp = &sm.cnt[ql];
-    volatile uint2* lst = glist;
-    const int c = *cntp;
-    if (c < LCAP) {
-        lst[c].x = __float_as_uint(sc); lst[c].y = (uint32_t)lin;
-        *cntp = c + 1;
-        if (c + 1 == LCAP) {
-            float m = sc;
-            for (int u = 0; u < LCAP - 1; ++u) m = fminf(m, __uint_as_float(lst[u].x));
-            *reinterpret_cast<volatile float*>(&sm.lmin[ql]) = m;
-            thr = fmaxf(thr, m);
-        }
-    } else {
-        float m1 = INFINITY, m2 = INFINITY; int p1 = 0;
-        for (int u = 0; u < LCAP; ++u) {
-            const float v = __uint_as_float(lst[u].x);
-            if (v < m1) { m2 = m1; m1 = v; p1 = u; } else if (v < m2) { m2 = v; }
-        }
-        if (sc > m1) {
-            lst[p1].x = __float_as_uint(sc); lst[p1].y = (uint32_t)lin;
-            m1 = fminf(m2, sc);
-        }
-        *reinterpret_cast<volatile float*>(&sm.lmin[ql]) = m1;
-        thr = fmaxf(thr, m1);
+// Candidate lists are PRIVATE to a scan thread (query, column slice, tile parity): plain appends to global memory, no lock and
+// no fence (nobody else reads them before the next inter-CTA barrier).  A full list (LCAP >= top_k entries) keeps its LCAP
+// largest scores, which keeps the selection exact for any input; that path only runs when > 32 scores of ONE thread's
+// ~500 columns pass the lower bound.
+__device__ __noinline__ float list_min(const uint2* lst) {
+    float m = INFINITY;
+    for (int u = 0; u < LCAP; ++u) m = fminf(m, __uint_as_float(__ldcg(&lst[u]).x));
+    return m;
+}
+__device__ __noinline__ float list_replace_min(uint2* lst, float sc, int lin) {
+    float m1 = INFINITY, m2 = INFINITY; int p1 = 0;
+    for (int u = 0; u < LCAP; ++u) {
+        const float v = __uint_as_float(__ldcg(&lst[u]).x);
+        if (v < m1) { m2 = m1; m1 = v; p1 = u; } else if (v < m2) { m2 = v; }
     }
-    __threadfence_block();
-    atomicExch(&sm.lock[ql], 0);
+    if (sc > m1) {
+        __stcg(&lst[p1], make_uint2(__float_as_uint(sc), (uint32_t)lin));
+        m1 = fminf(m2, sc);
+    }
+    return m1;                                                // the smallest listed score: nothing below it matters any more
+}
+__device__ __forceinline__ void list_append(uint2* lst, int& cnt, float& thr, float sc, int lin) {
+    if (cnt < LCAP) {
+        __stcg(&lst[cnt], make_uint2(__float_as_uint(sc), (uint32_t)lin));
+        if (++cnt == LCAP) thr = fmaxf(thr, list_min(lst));
+    } else {
+        thr = fmaxf(thr, list_replace_min(lst, sc, lin));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -329,33 +349,78 @@ __device__ int warp_compact_ge(uint64_t* scr, int n, uint64_t thr, int lane) {
     }
     return w;
 }
-// gather the per-slice lists of query q into scr, never holding more than SCR_CAP entries: when the scratch would overflow it
-// is first reduced to its `keep` largest keys (exact).  min_score_ord: entries below it are dropped (T-shard selection).
+// gather the candidate lists of query q (2 * nslice1 thread lists) into scr.  Fast path: every lane reads the counts of its
+// lists at once and copies their entries to its own offset (one L2 round trip per step instead of one per list).  Lists that
+// together exceed the scratch fall back to a sequential gather that first reduces the scratch to its `keep` largest keys
+// (exact).  min_score_ord: entries below it are dropped (T-shard selection).
 __device__ int warp_gather_lists(const K1Params& p, int q, uint64_t* scr, int keep, uint32_t min_score_ord, int lane) {
+    const int nlists = 2 * p.nslice1;                         // (column slice, tile parity); <= 64
+    const int* cntp = p.lcnt + (size_t)q * nlists;
+    const uint2* lbase = p.lists + (size_t)q * nlists * LCAP;
+    const int c0 = (lane < nlists) ? min(LCAP, __ldcg(cntp + lane)) : 0;
+    const int c1 = (lane + 32 < nlists) ? min(LCAP, __ldcg(cntp + lane + 32)) : 0;
+    int x0 = c0, x1 = c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
+        if (lane >= o) { x0 += y0; x1 += y1; }
+    }
+    const int tot0 = __shfl_sync(0xffffffffu, x0, 31), total = tot0 + __shfl_sync(0xffffffffu, x1, 31);
     int n = 0;
-    for (int s = 0; s < p.nslice1; ++s) {
-        const int c = min(LCAP, __ldcg(p.lcnt + (size_t)q * p.nslice1 + s));
-        if (c == 0) continue;
-        if (n + c > SCR_CAP) {
-            if (n > keep) {
+    if (total <= SCR_CAP) {
+        const int off0 = x0 - c0, off1 = tot0 + x1 - c1;
+        // loads in batches of 4 per list (independent L2 requests in flight), then the shared-memory stores
+        const uint2* l0 = lbase + (size_t)lane * LCAP;
+        const uint2* l1 = lbase + (size_t)(lane + 32) * LCAP;
+        for (int e0 = 0; e0 < max(c0, c1); e0 += 4) {
+            uint2 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a[u] = (e0 + u < c0) ? __ldcg(l0 + e0 + u) : make_uint2(0u, 0u);
+                b[u] = (e0 + u < c1) ? __ldcg(l1 + e0 + u) : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (e0 + u < c0) scr[off0 + e0 + u] = make_key(a[u].x, a[u].y);
+                if (e0 + u < c1) scr[off1 + e0 + u] = make_key(b[u].x, b[u].y);
+            }
+        }
+        n = total;
+        __syncwarp();
+    } else {
+        for (int s = 0; s < nlists; ++s) {
+            const int c = min(LCAP, __ldcg(cntp + s));
+            if (c == 0) continue;
+            if (n + c > SCR_CAP && n > keep) {
                 const uint64_t kth = warp_kth_key(scr, n, keep, lane);
                 __syncwarp();
                 n = warp_compact_ge(scr, n, kth, lane);
             }
+            if (lane < c) { const uint2 ent = __ldcg(lbase + (size_t)s * LCAP + lane); scr[n + lane] = make_key(ent.x, ent.y); }
+            n += c;
+            __syncwarp();
         }
-        const uint2* src = p.lists + ((size_t)q * p.nslice1 + s) * LCAP;
-        for (int base = 0; base < c; base += 32) {
-            const int e = base + lane;
-            uint2 ent = make_uint2(0u, 0u);
-            bool ok = e < c;
-            if (ok) { ent = __ldcg(src + e); ok = f2ord(__uint_as_float(ent.x)) >= min_score_ord; }
-            const unsigned b = __ballot_sync(0xffffffffu, ok);
-            if (ok) scr[n + __popc(b & ((1u << lane) - 1u))] = make_key(ent.x, ent.y);
-            n += __popc(b);
-        }
-        __syncwarp();
     }
+    if (min_score_ord != 0u) n = warp_compact_ge(scr, n, static_cast<uint64_t>(min_score_ord) << 32, lane);
     return n;
+}
+// The `want` largest of scr[0..n) (n <= 128, distinct keys) in DESCENDING order into out[0..min(n, want)): every lane ranks its
+// (up to 4) keys against all n by broadcast reads -- no cross-lane traffic, independent iterations.  Returns min(n, want).
+__device__ int warp_select_sorted(const uint64_t* scr, int n, int want, uint64_t* out, int lane) {
+    uint64_t mine[4];
+    int rank[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const int e = lane + 32 * i; mine[i] = (e < n) ? scr[e] : ~0ull; rank[i] = 0; }
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+        const uint64_t kj = scr[j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rank[i] += (kj > mine[i]) ? 1 : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (lane + 32 * i < n && rank[i] < want) out[rank[i]] = mine[i];
+    __syncwarp();
+    return min(n, want);
 }
 // descending bitonic sort of one key per lane (32 keys)
 __device__ __forceinline__ uint64_t warp_sort_desc(uint64_t key, int lane) {
@@ -374,12 +439,121 @@ __device__ __forceinline__ uint64_t warp_sort_desc(uint64_t key, int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// score scan of one 128-column key tile by one thread (= one query): 8 blocks of 16 columns, the TMEM load of the next block
+// in flight while the current one is processed.  Compile-time variants keep the hot loop small (instruction cache!):
+//   SWEEP 0: slot maxima   SWEEP 1: collect scores above thr     FULL: every column of the tile is valid     DBG: test dump
+// ---------------------------------------------------------------------------------------------
+struct ScanCtx {
+    float bsq8;
+    float thr;
+    uint2* glist;
+    int cnt;
+    int lin0;
+    int lo, hi;
+    float* dbg;            // column 0 of this tile, this query (DBG only)
+    ptrdiff_t dbg_stride;
+};
+
+// a thread whose list is (nearly) full: per-score appends with the replace-min rule (exact top-LCAP of the thread's columns).
+// Everything by value: taking the address of the caller's score registers would move them to local memory.
+struct SlowRet { int cnt; float thr; };
+__device__ __noinline__ SlowRet scan_block_slow(uint2* glist, int cnt, float thr, int lin, float s0, float s1, float s2, float s3, float s4,
+                                                float s5, float s6, float s7, float s8, float s9, float s10, float s11, float s12, float s13,
+                                                float s14, float s15) {
+    const float sc[16] = {s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15};
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (sc[j] > thr) list_append(glist, cnt, thr, sc[j], lin + j);
+    SlowRet r; r.cnt = cnt; r.thr = thr;
+    return r;
+}
+
+template <int SWEEP, bool FULL, bool DBG>
+__device__ __forceinline__ void scan_block16(const uint32_t (&r)[16], const float* msp, int c, float (&slot)[NSLOT], ScanCtx& cx) {
+    float sc[16];
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+        const float4 f = *reinterpret_cast<const float4*>(msp + c * 16 + j);
+        sc[j] = score2(r[j], cx.bsq8, f.x); sc[j + 1] = score2(r[j + 1], cx.bsq8, f.y);
+        sc[j + 2] = score2(r[j + 2], cx.bsq8, f.z); sc[j + 3] = score2(r[j + 3], cx.bsq8, f.w);
+    }
+    if (!FULL) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = c * 16 + j;
+            sc[j] = (n >= cx.lo && n < cx.hi) ? sc[j] : -INFINITY;
+        }
+    }
+    if (SWEEP == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) slot[j] = fmax3(slot[j], sc[j], sc[j + 8]);      // 8 slots, one FMNMX3 per two scores
+        if (DBG) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (sc[j] != -INFINITY) cx.dbg[(ptrdiff_t)(c * 16 + j) * cx.dbg_stride] = sc[j];
+        }
+    } else {
+        // maxima of the four 4-column groups (FMNMX3), then of the block; the append code below only runs for the groups in
+        // which some lane of the warp is above its threshold (~20 % of them), and is branch-free (predicated store + add)
+        const float g0 = fmaxf(fmax3(sc[0], sc[1], sc[2]), sc[3]), g1 = fmaxf(fmax3(sc[4], sc[5], sc[6]), sc[7]);
+        const float g2 = fmaxf(fmax3(sc[8], sc[9], sc[10]), sc[11]), g3 = fmaxf(fmax3(sc[12], sc[13], sc[14]), sc[15]);
+        const float m = fmaxf(fmax3(g0, g1, g2), g3);
+        if (__any_sync(0xffffffffu, m > cx.thr)) {
+            const int lin = cx.lin0 + c * 16;
+            // warp-uniform votes first (the per-lane branch on the list fill below must not contain warp collectives)
+            const bool v0 = __any_sync(0xffffffffu, g0 > cx.thr), v1 = __any_sync(0xffffffffu, g1 > cx.thr);
+            const bool v2 = __any_sync(0xffffffffu, g2 > cx.thr), v3 = __any_sync(0xffffffffu, g3 > cx.thr);
+            if (cx.cnt <= LCAP - 16) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const bool vg = g == 0 ? v0 : (g == 1 ? v1 : (g == 2 ? v2 : v3));
+                    if (vg) {
+#pragma unroll
+                        for (int j = 4 * g; j < 4 * g + 4; ++j) {
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
+                                "setp.gt.f32 p, %1, %2;\n\t"
+                                "mad.wide.s32 a, %0, 8, %3;\n\t"
+                                "@p st.global.cg.v2.b32 [a], {%4, %5};\n\t"
+                                "@p add.s32 %0, %0, 1;\n\t}"
+                                : "+r"(cx.cnt)
+                                : "f"(sc[j]), "f"(cx.thr), "l"(cx.glist), "r"(__float_as_uint(sc[j])), "r"(lin + j)
+                                : "memory");
+                        }
+                    }
+                }
+            } else if (m > cx.thr) {
+                const SlowRet r = scan_block_slow(cx.glist, cx.cnt, cx.thr, lin, sc[0], sc[1], sc[2], sc[3], sc[4], sc[5], sc[6], sc[7], sc[8],
+                                                  sc[9], sc[10], sc[11], sc[12], sc[13], sc[14], sc[15]);
+                cx.cnt = r.cnt; cx.thr = r.thr;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int SWEEP, bool FULL, bool DBG>
+__device__ __forceinline__ void scan_tile(uint32_t trow, const float* msp, float (&slot)[NSLOT], ScanCtx& cx) {
+    uint32_t ra[16], rb[16];
+    tmem_ld_32x32b_x16(trow, ra);
+#pragma unroll 1
+    for (int c = 0; c < 8; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32b_x16(trow + (c + 1) * 16, rb);
+        scan_block16<SWEEP, FULL, DBG>(ra, msp, c, slot, cx);
+        tmem_ld_wait();
+        if (c + 2 < 8) tmem_ld_32x32b_x16(trow + (c + 2) * 16, ra);
+        scan_block16<SWEEP, FULL, DBG>(rb, msp, c + 1, slot, cx);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1)
 k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // aligned base as an OFFSET from the extern array: the compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     SweepSmem& sw = *reinterpret_cast<SweepSmem*>(base);
     ReadSmem& rd = *reinterpret_cast<ReadSmem*>(base);
     CommonSmem& cm = *reinterpret_cast<CommonSmem*>(base + SMEM_MAIN);
@@ -421,6 +595,12 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
     if (threadIdx.x < sizeof(K1Seg) / 4) reinterpret_cast<uint32_t*>(&cm.sg)[threadIdx.x] = reinterpret_cast<const uint32_t*>(p.seg)[threadIdx.x];
     __syncthreads();
     const K1Seg& sg = cm.sg;
+    K1_STAMP(0);
+    const bool want_usage = p.do_usage && (p.mode & MODE_READOUT) && (sg.usage[0] || sg.usage[1] || sg.usage[2]);
+    if (want_usage) {                                         // consumed after the grid barrier that opens the readout
+        const int ncol = sg.t64[sg.nseg] * TK;
+        for (int i = cta * NTHREADS + threadIdx.x; i < ncol; i += G * NTHREADS) p.uacc[i] = 0ull;
+    }
 
     unsigned pair_uses = 0, grid_uses = 0;
 
@@ -430,17 +610,18 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
     const int t_end = (int)(((long long)total128 * (slice + 1)) / S1);
     const int nt = in_sweep ? (t_end - t_begin) : 0;
     unsigned* pair_ctr = p.ctr + 8 + pair;
-    int sweeps_done = 0;
+    int done_it = 0, done_uses[2] = {0, 0};
     bool q_loaded = false;
 
     for (int sweep = 0; sweep < 2; ++sweep) {
         const int this_mode = sweep == 0 ? MODE_SWEEP_A : MODE_SWEEP_B;
         if (!(p.mode & this_mode)) continue;
         if (in_sweep) {
-            const int it0 = sweeps_done * nt;                 // mbarrier phases continue across the two sweeps
-            // uses of S buffer b before this sweep: tiles i < nt with (i & 1) == b, per completed sweep
-            const int uses0[2] = {sweeps_done * ((nt + 1) >> 1), sweeps_done * (nt >> 1)};
-            if (sweep == 1 && threadIdx.x < QPAIR) { sw.cnt[threadIdx.x] = 0; sw.lock[threadIdx.x] = 0; sw.lmin[threadIdx.x] = -INFINITY; }
+            // sweep A may sample every a_stride-th key tile; iteration i of a sweep works on tile t_begin + i * tstride
+            const int tstride = (sweep == 0) ? p.a_stride : 1;
+            const int n_it = (nt + tstride - 1) / tstride;
+            const int it0 = done_it;                          // mbarrier phases continue across the two sweeps
+            const int uses0[2] = {done_uses[0], done_uses[1]};   // uses of S buffer b (iterations with (i & 1) == b) so far
             __syncthreads();
             if (warp == 0) {
                 if (lane == 0) {
@@ -451,29 +632,39 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                             tma_load_2d(sw.q[h][1], &maps.q, &cm.qfull, 64, (pair * 2 + h) * TQ);
                         }
                     }
-                    for (int i = 0; i < nt; ++i) {
+                    long long c_wait = 0;
+                    for (int i = 0; i < n_it; ++i) {
                         int s, col, lo, hi;
-                        locate_tile128(sg, t_begin + i, s, col, lo, hi);
+                        locate_tile128(sg, t_begin + i * tstride, s, col, lo, hi);
                         const int it = it0 + i, st = it % P1_KSTAGES, ph = (it / P1_KSTAGES) & 1;
                         const uint32_t ms_bytes = (uint32_t)min(TN, sg.cap[s] - col) * 4u;
+                        const long long tw = K1_CLK();
                         mbar_wait(&cm.kempty[st], ph ^ 1, 2);
+                        K1_ACC(c_wait, tw);
                         mbar_expect_tx(&cm.kfull[st], 2 * TN * 128 + ms_bytes);
                         const CUtensorMap* km = &maps.k[sg.bank[s]];
                         tma_load_2d(sw.st[st].k[0], km, &cm.kfull[st], 0, col);
                         tma_load_2d(sw.st[st].k[1], km, &cm.kfull[st], 64, col);
                         bulk_g2s(sw.st[st].ms, sg.shr[s] + col, ms_bytes, &cm.kfull[st]);
                     }
+                    K1_TRACE_OUT(0, sweep, c_wait, n_it, 0);
                 }
             } else if (warp == 1) {
                 if (lane == 0) {
                     constexpr uint32_t idesc = make_idesc_f16(TQ, TN);
                     if (!q_loaded) mbar_wait(&cm.qfull, 0, 1);
-                    for (int i = 0; i < nt; ++i) {
+                    long long c_kfull = 0, c_sempty = 0, c_issue = 0;
+                    for (int i = 0; i < n_it; ++i) {
                         const int it = it0 + i, st = it % P1_KSTAGES, ph = (it / P1_KSTAGES) & 1;
                         const int b = i & 1, use = uses0[b] + (i >> 1);
+                        long long tw = K1_CLK();
                         mbar_wait(&cm.kfull[st], ph, 3);
+                        K1_ACC(c_kfull, tw);
                         for (int h = 0; h < nqh; ++h) {
+                            tw = K1_CLK();
                             mbar_wait(&cm.sempty[h][b], (use & 1) ^ 1, 4);
+                            K1_ACC(c_sempty, tw);
+                            tw = K1_CLK();
                             tc_fence_after();
 #pragma unroll
                             for (int kh = 0; kh < 2; ++kh)
@@ -484,9 +675,11 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                                     mma_f16_ss(tmem + (h * 2 + b) * TN, a, bd, idesc, (kh | j) ? 1u : 0u);
                                 }
                             mma_commit(&cm.sfull[h][b]);
+                            K1_ACC(c_issue, tw);
                         }
                         mma_commit(&cm.kempty[st]);
                     }
+                    K1_TRACE_OUT(1, sweep, c_kfull, c_sempty, c_issue);
                 }
             } else {
                 // scan warps: warp group wg = (q-tile h, tile parity b); a thread owns one query (TMEM lane) and sees
@@ -501,117 +694,94 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                     float slot[NSLOT];
 #pragma unroll
                     for (int j = 0; j < NSLOT; ++j) slot[j] = -INFINITY;
-                    float thr = -INFINITY;
+                    ScanCtx cx;
+                    cx.bsq8 = bsq8; cx.thr = -INFINITY; cx.cnt = 0; cx.dbg = nullptr; cx.dbg_stride = 0;
                     if (sweep == 1) {
                         const float t = (p.mode & MODE_EXT_TAU) ? p.tau_ext[q] : __ldcg(p.tau_lo + q);
-                        thr = (t == -INFINITY) ? -INFINITY : ((t == INFINITY) ? FLT_MAX : __uint_as_float(
+                        cx.thr = (t == -INFINITY) ? -INFINITY : ((t == INFINITY) ? FLT_MAX : __uint_as_float(
                                   t > 0.f ? __float_as_uint(t) - 1u : (t < 0.f ? __float_as_uint(t) + 1u : 0x80000001u)));   // pred(tau_lo)
                     }
-                    uint2* glist = p.lists + ((size_t)q * S1 + slice) * LCAP;      // this (query, slice)'s candidate list
+                    cx.glist = p.lists + (((size_t)q * S1 + slice) * 2 + b) * LCAP;          // this thread's candidate list
+#ifdef K1_NOHIT
+                    if (sweep == 1) cx.thr = FLT_MAX;      // experiment: cost of sweep B without any candidate
+#endif
+                    long long c_wait = 0, c_scan = 0;
                     const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16) + (h * 2 + b) * TN;
-                    for (int i = b; i < nt; i += 2) {
+                    for (int i = b; i < n_it; i += 2) {
                         int s, col, lo, hi;
-                        locate_tile128(sg, t_begin + i, s, col, lo, hi);
+                        locate_tile128(sg, t_begin + i * tstride, s, col, lo, hi);
                         const int use = uses0[b] + (i >> 1);
                         const int it = it0 + i, st = it % P1_KSTAGES, ph = (it / P1_KSTAGES) & 1;
                         const float* msp = sw.st[st].ms;
-                        if (sweep == 1) thr = fmaxf(thr, *reinterpret_cast<volatile float*>(&sw.lmin[ql]));
+                        long long tw = K1_CLK();
                         mbar_wait(&cm.kfull[st], ph, 6);              // the shrinkage slice arrived with the key tile
                         mbar_wait(&cm.sfull[h][b], use & 1, 5);
+                        K1_ACC(c_wait, tw);
+                        tw = K1_CLK();
                         tc_fence_after();
                         const bool full_tile = (lo <= 0) && (hi >= TN);
                         const int lin0 = linear_col(sg, s, col);
-#pragma unroll 1
-                        for (int c = 0; c < 4; ++c) {
-                            uint32_t r[32];
-                            tmem_ld_32x32b_x32(trow + c * 32, r);
-                            float ms[32];
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 f = *reinterpret_cast<const float4*>(msp + c * 32 + j);
-                                ms[j] = f.x; ms[j + 1] = f.y; ms[j + 2] = f.z; ms[j + 3] = f.w;
-                            }
-                            tmem_ld_wait();
-                            float sc[32];
-                            if (full_tile) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) sc[j] = score2(r[j], bsq8, ms[j]);
+                        cx.lin0 = lin0; cx.lo = lo; cx.hi = hi;
+                        if (sweep == 0) {
+                            if (p.dbg) {                       // tests / selector only (warp-uniform)
+                                cx.dbg = p.dbg + ((ptrdiff_t)sg.col0[s] + (col - sg.begin[s])) * (ptrdiff_t)p.hw_pad + q;
+                                cx.dbg_stride = p.hw_pad;
+                                scan_tile<0, false, true>(trow, msp, slot, cx);
+                            } else if (full_tile) {
+                                scan_tile<0, true, false>(trow, msp, slot, cx);
                             } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    const int n = c * 32 + j;
-                                    sc[j] = (n >= lo && n < hi) ? score2(r[j], bsq8, ms[j]) : -INFINITY;
-                                }
+                                scan_tile<0, false, false>(trow, msp, slot, cx);
                             }
-                            if (sweep == 0) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) slot[j & (NSLOT - 1)] = fmaxf(slot[j & (NSLOT - 1)], sc[j]);
-                                if (p.dbg) {                   // tests / selector only (warp-uniform)
-                                    float* dbg = p.dbg + ((ptrdiff_t)sg.col0[s] + (col + c * 32 - sg.begin[s])) * (ptrdiff_t)p.hw_pad + q;
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) if (sc[j] != -INFINITY) dbg[(ptrdiff_t)j * p.hw_pad] = sc[j];
-                                }
-                            } else {
-                                uint32_t h0 = 0u, h1 = 0u, h2 = 0u, h3 = 0u;
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    h0 |= (sc[j] > thr) ? (1u << j) : 0u;
-                                    h1 |= (sc[8 + j] > thr) ? (256u << j) : 0u;
-                                    h2 |= (sc[16 + j] > thr) ? (65536u << j) : 0u;
-                                    h3 |= (sc[24 + j] > thr) ? (16777216u << j) : 0u;
-                                }
-                                const uint32_t hit = h0 | h1 | h2 | h3;
-                                uint32_t any = __reduce_or_sync(0xffffffffu, hit);
-                                while (any) {                  // ~2 columns per 32x32 block: re-read that column for the warp
-                                    const int j = __ffs(any) - 1;
-                                    any &= any - 1u;
-                                    uint32_t rv;
-                                    tmem_ld_32x32b_x1(trow + c * 32 + j, rv);
-                                    tmem_ld_wait();
-                                    if ((hit >> j) & 1u) {
-                                        const float v = score2(rv, bsq8, msp[c * 32 + j]);
-                                        if (v > thr) list_append(v, lin0 + c * 32 + j, ql, sw, glist, thr);
-                                    }
-                                    __syncwarp();
-                                }
-                            }
+                        } else {
+                            if (full_tile) scan_tile<1, true, false>(trow, msp, slot, cx);
+                            else scan_tile<1, false, false>(trow, msp, slot, cx);
                         }
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) { mbar_arrive(&cm.sempty[h][b]); mbar_arrive(&cm.kempty[st]); }
+                        K1_ACC(c_scan, tw);
                     }
+                    if (lane == 0) K1_TRACE_OUT(2 + ww, sweep, c_wait, c_scan, (n_it - b + 1) >> 1);
                     if (sweep == 0) {
                         // 32 slot maxima per (slice, query): 16 from each tile parity
                         float* dst = p.candA + ((size_t)q * S1 + slice) * (2 * NSLOT) + b * NSLOT;
 #pragma unroll
                         for (int u = 0; u < NSLOT; u += 4) *reinterpret_cast<float4*>(dst + u) = make_float4(slot[u], slot[u + 1], slot[u + 2], slot[u + 3]);
+                    } else {
+                        p.lcnt[((size_t)q * S1 + slice) * 2 + b] = cx.cnt;
                     }
                 }
             }
             __syncthreads();
-            if (sweep == 1 && threadIdx.x < QPAIR) p.lcnt[((size_t)(pair * QPAIR + threadIdx.x)) * S1 + slice] = sw.cnt[threadIdx.x];
+            K1_STAMP(sweep == 0 ? 1 : 4);
             q_loaded = true;
-            ++sweeps_done;
+            done_it += n_it; done_uses[0] += (n_it + 1) >> 1; done_uses[1] += n_it >> 1;
 
             // ---------------------------------------------------------------- merge A: tau_lo = k-th largest slot maximum
             if (sweep == 0) {
                 cta_group_barrier(pair_ctr, ++pair_uses * S1, 40);
+                K1_STAMP(2);
                 if (warp >= 2) {
                     for (int ql = slice + ww * S1; ql < nqh * TQ; ql += NWORK * S1) {
                         const int q = pair * QPAIR + ql;
                         float* out = p.tau_lo;
                         if (q >= p.hw) { if (lane == 0) out[q] = INFINITY; continue; }      // padded queries never select anything
-                        uint32_t v[MAX_SLICE1];
-                        const float* src = p.candA + (size_t)q * S1 * 32;
-#pragma unroll
-                        for (int u = 0; u < MAX_SLICE1; ++u) v[u] = (u < S1) ? f2ord(__ldcg(src + u * 32 + lane)) : 0u;
+                        // every lane keeps the two largest of its S1 slot maxima; the k-th largest of those 64 values is
+                        // still a lower bound of the k-th largest score (real scores of distinct columns) and ~3 ranks looser
+                        const int nval = S1 * 2 * NSLOT;
+                        const float* src = p.candA + (size_t)q * nval;
+                        float m1 = -INFINITY, m2 = -INFINITY;
+                        for (int u = lane; u < nval; u += 32) {
+                            const float v = __ldcg(src + u);
+                            m2 = fmaxf(m2, fminf(m1, v));
+                            m1 = fmaxf(m1, v);
+                        }
+                        const uint32_t o1 = f2ord(m1), o2 = f2ord(m2);
                         uint32_t t = 0u;
 #pragma unroll 1
                         for (int bit = 31; bit >= 0; --bit) {
                             const uint32_t trial = t | (1u << bit);
-                            int c = 0;
-#pragma unroll
-                            for (int u = 0; u < MAX_SLICE1; ++u) c += (v[u] >= trial) ? 1 : 0;
+                            int c = ((o1 >= trial) ? 1 : 0) + ((o2 >= trial) ? 1 : 0);
                             c = __reduce_add_sync(0xffffffffu, c);
                             if (c >= p.top_k) t = trial;
                         }
@@ -621,8 +791,10 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                     }
                 }
                 if (p.mode & MODE_SWEEP_B) cta_group_barrier(pair_ctr, ++pair_uses * S1, 41);
+                K1_STAMP(3);
             } else {
                 cta_group_barrier(pair_ctr, ++pair_uses * S1, 42);
+                K1_STAMP(5);
             }
         }
     }
@@ -639,17 +811,26 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
             }
             const bool ext = (p.mode & MODE_EXT_TAU) != 0;
             const uint32_t min_ord = (ext && (p.mode & MODE_SELECT)) ? f2ord(p.tau_ext[q]) : 0u;
+            long long tw = K1_CLK(), c_g = 0, c_k = 0, c_r = 0;
             int n = warp_gather_lists(p, q, scr, LISTK, min_ord, lane);
             __syncwarp();
+            K1_ACC(c_g, tw); tw = K1_CLK();
             const int want = (p.mode & MODE_EXPORT32) ? LISTK : (ext ? LISTK : p.top_k);
-            if (n > want) {
+            uint64_t key;
+            if (n <= 128) {
+                uint64_t* out = scr + SCR_CAP / 2;             // n <= 128 leaves the upper half of the scratch free
+                n = warp_select_sorted(scr, n, want, out, lane);
+                key = (lane < n) ? out[lane] : 0ull;
+                K1_ACC(c_k, tw); tw = K1_CLK();
+            } else {
                 const uint64_t kth = warp_kth_key(scr, n, want, lane);
                 __syncwarp();
                 n = warp_compact_ge(scr, n, kth, lane);
+                __syncwarp();
+                K1_ACC(c_k, tw); tw = K1_CLK();
+                key = (lane < n) ? scr[lane] : 0ull;
+                key = warp_sort_desc(key, lane);
             }
-            __syncwarp();
-            uint64_t key = (lane < n) ? scr[lane] : 0ull;
-            key = warp_sort_desc(key, lane);
             const bool have = key != 0ull;
             const float s = have ? ord2f(static_cast<uint32_t>(key >> 32)) : -INFINITY;
             const uint32_t lin = 0xffffffffu - static_cast<uint32_t>(key & 0xffffffffu);
@@ -667,20 +848,20 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                 }
                 const float pv = ex * inv;
                 p.fin[(size_t)q * LISTK + lane] = have ? make_uint2(lin, __float_as_uint(pv)) : make_uint2(0xffffffffu, 0u);
-                if (have && p.do_usage) {
-                    int sgi, col;
-                    unlinear_col(sg, (int)lin, sgi, col);
-                    if (sg.usage[sgi]) atomicAdd(sg.usage[sgi] + col, pv);
-                }
             }
             __syncwarp();
+            K1_ACC(c_r, tw);
+            if (lane == 0) K1_TRACE_OUT(18 + ww, 0, c_g, c_k, c_r);
         }
     }
 
     // ------------------------------------------------------------------ readout: O[q, c] += P[q, n] V[n, c]
     if (p.mode & MODE_READOUT) {
         fence_proxy_async_smem();                             // the merge scratch (generic proxy) aliases the TMA / UMMA buffers below
-        cta_group_barrier(p.ctr, ++grid_uses * G, 43);
+        __syncthreads();
+        K1_STAMP(6);
+        cta_group_barrier(p.ctr, ++grid_uses * G, 43, p.timeline + (size_t)blockIdx.x * 16);
+        K1_STAMP(7);
         pdl_launch_dependents();
         const int KT = sg.t64[sg.nseg];
         // zero both P buffers once; afterwards only the listed entries are written and cleared again
@@ -780,31 +961,40 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                         if (kt >= kb && kt < ke) {
                             const uint32_t pos = atomicAdd(&rd.cur[kt - kb], 1u);
                             const int ql = i / LISTK;            // query inside the pair
-                            const uint32_t where = ((uint32_t)(ql >> 7) << 13) | ((uint32_t)(ql & 127) << 6) | (e.x & 63u);
-                            const __half wv = __float2half_rn(__uint_as_float(e.y));
-                            rd.ent[pos] = where | ((uint32_t)__half_as_ushort(wv) << 16);
+                            rd.entp[pos] = (uint16_t)(((uint32_t)(ql >> 7) << 13) | ((uint32_t)(ql & 127) << 6) | (e.x & 63u));
+                            rd.entw[pos] = __uint_as_float(e.y);
                         }
                     }
                     asm volatile("bar.sync 1, 512;" ::: "memory");
                     if (ww < 2) {
                         const int pb = ww;
+                        const bool usage_item = want_usage && chalf == 0 && obj == 0;     // one CTA per (query pair, k-tile) sums the usage
+                        auto p_addr = [&](uint32_t x) -> uint16_t* {        // element (q-tile, row, column) of the swizzled P tile
+                            const uint32_t r = (x >> 6) & 127u, c = x & 63u;
+                            return reinterpret_cast<uint16_t*>(&rd.p[pb][(x >> 13) & 1u][r * 128 + (((c >> 3) ^ (r & 7u)) << 4) + (c & 7u) * 2]);
+                        };
                         for (int n = kb - k0; n < ke - k0; ++n) {
                             const int g = g0 + n;
                             if ((g & 1) != pb) continue;
                             const int use = g >> 1;
-                            mbar_wait(&cm.pempty[pb], (use & 1) ^ 1, 11);
-                            for (int e = prev_b + lane; e < prev_e; e += 32) {      // clear what the previous use of this buffer set
-                                const uint32_t x = rd.ent[e] & 0xffffu;
-                                const uint32_t r = (x >> 6) & 127u, c = x & 63u;
-                                *reinterpret_cast<__half*>(&rd.p[pb][x >> 13][r * 128 + (((c >> 3) ^ (r & 7u)) << 4) + (c & 7u) * 2]) = __float2half(0.f);
-                            }
                             const int li = (k0 + n) - kb;
                             const int eb = rd.off[li], ee = rd.off[li + 1];
-                            for (int e = eb + lane; e < ee; e += 32) {
-                                const uint32_t x = rd.ent[e];
-                                const uint32_t r = (x >> 6) & 127u, c = x & 63u;
-                                *reinterpret_cast<uint16_t*>(&rd.p[pb][(x >> 13) & 1u][r * 128 + (((c >> 3) ^ (r & 7u)) << 4) + (c & 7u) * 2]) = (uint16_t)(x >> 16);
+                            if (usage_item) {
+                                // column sums of this (query pair, k-tile) in 2^-40 fixed point: integer adds commute, so the
+                                // result does not depend on the order in which the entries were bucketed
+                                unsigned long long* ut = rd.utile[pb];
+                                ut[lane] = 0ull; ut[lane + 32] = 0ull;
+                                __syncwarp();
+                                for (int e = eb + lane; e < ee; e += 32)
+                                    atomicAdd(&ut[rd.entp[e] & 63u], (unsigned long long)(rd.entw[e] * 1099511627776.f));
+                                __syncwarp();
+                                unsigned long long* ua = p.uacc + (size_t)(k0 + n) * TK;
+                                if (ut[lane]) atomicAdd(ua + lane, ut[lane]);
+                                if (ut[lane + 32]) atomicAdd(ua + lane + 32, ut[lane + 32]);
                             }
+                            mbar_wait(&cm.pempty[pb], (use & 1) ^ 1, 11);
+                            for (int e = prev_b + lane; e < prev_e; e += 32) *p_addr(rd.entp[e]) = 0;      // clear the previous use of this buffer
+                            for (int e = eb + lane; e < ee; e += 32) *p_addr(rd.entp[e]) = __half_as_ushort(__float2half_rn(rd.entw[e]));
                             prev_b = eb; prev_e = ee;
                             fence_proxy_async_smem();
                             __syncwarp();
@@ -812,16 +1002,11 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                         }
                         // end of the batch: the entry table is about to be rebuilt -> clear this buffer's last entries now
                         if (prev_e > prev_b) {
-                            // the last use of buffer pb in this batch
                             int last_g = -1;
                             for (int n = ke - k0 - 1; n >= kb - k0; --n) if (((g0 + n) & 1) == pb) { last_g = g0 + n; break; }
                             if (last_g >= 0) {
                                 mbar_wait(&cm.pempty[pb], (last_g >> 1) & 1, 12);
-                                for (int e = prev_b + lane; e < prev_e; e += 32) {
-                                    const uint32_t x = rd.ent[e] & 0xffffu;
-                                    const uint32_t r = (x >> 6) & 127u, c = x & 63u;
-                                    *reinterpret_cast<__half*>(&rd.p[pb][x >> 13][r * 128 + (((c >> 3) ^ (r & 7u)) << 4) + (c & 7u) * 2]) = __float2half(0.f);
-                                }
+                                for (int e = prev_b + lane; e < prev_e; e += 32) *p_addr(rd.entp[e]) = 0;
                                 fence_proxy_async_smem();
                             }
                             prev_b = prev_e = 0;
@@ -860,42 +1045,83 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
         }
 
         // ---------------------------------------------------------------- reduce the column-slice partials
+        __syncthreads();
+        K1_STAMP(8);
         cta_group_barrier(p.ctr, ++grid_uses * G, 44);
+        K1_STAMP(9);
         if (warp >= 2) {
-            float* tr = reinterpret_cast<float*>(&rd.v[0][0]) + (size_t)ww * 32 * 33;
-            const int qblocks = p.hw_pad / 32;
-            const int tiles = p.n_obj * qblocks * 16;
-            for (int t = cta * NWORK + ww; t < tiles; t += G * NWORK) {
-                const int obj = t / (qblocks * 16);
-                const int rem = t - obj * qblocks * 16;
-                const int qb = rem >> 4, cb = rem & 15;
-                const int q0 = qb * 32, c0 = cb * 32;
-                const int rpair = q0 / QPAIR, ql0 = q0 - rpair * QPAIR;
-                const int chalf = cb >> 3;
+            // (1) NHWC outputs: one warp per (object, query, 128-channel quarter), a lane sums 4 channels over the slices
+            //     (independent 16-byte loads, 512 contiguous bytes per warp and slice)
+            const int units = p.n_obj * p.hw_pad * 4;
+            for (int u = cta * NWORK + ww; u < units; u += G * NWORK) {
+                const int obj = u / (p.hw_pad * 4);
+                const int rem = u - obj * p.hw_pad * 4;
+                const int q = rem >> 2, cq = rem & 3;
+                const int rpair = q / QPAIR, ql = q - rpair * QPAIR;
+                const int chalf = cq >> 1;
                 const int row = ((rpair * p.n_obj + obj) << 1) | chalf;
                 int item0, nsl;
                 if (p.n_rows <= MAX_ROWS_TABLE) { item0 = cm.row_item0[row]; nsl = p.row_slices[row]; } else { item0 = row; nsl = 1; }
-                const float* src = p.partial + (size_t)item0 * (QPAIR * 256) + (size_t)ql0 * 256 + (c0 & 255) + lane;
-                const int oo = p.obj_begin + obj;
+                const float4* src = reinterpret_cast<const float4*>(p.partial + (size_t)item0 * (QPAIR * 256) + (size_t)ql * 256 + (cq & 1) * 128) + lane;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-                for (int qq = 0; qq < 32; ++qq) {
-                    float acc = 0.f;
-                    for (int s = 0; s < nsl; ++s) acc += __ldcg(src + (size_t)s * (QPAIR * 256) + qq * 256);
-                    const int q = q0 + qq;
-                    if (p.out_hwc && q < p.hw) p.out_hwc[((size_t)oo * p.hw + q) * XM_CV + c0 + lane] = __float2half_rn(acc);
-                    tr[qq * 33 + lane] = acc;
+                for (int s = 0; s < nsl; ++s) {
+                    const float4 f = __ldcg(src + (size_t)s * (QPAIR * 256 / 4));
+                    acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
                 }
-                __syncwarp();
-                if (p.out_chw || p.out_f32) {
-                    const int q = q0 + lane;
-#pragma unroll 4
-                    for (int cc = 0; cc < 32; ++cc) {
-                        const float v = tr[lane * 33 + cc];
-                        if (p.out_chw && q < p.hw) p.out_chw[((size_t)oo * XM_CV + c0 + cc) * p.hw + q] = __float2half_rn(v);
-                        if (p.out_f32) p.out_f32[((size_t)obj * XM_CV + c0 + cc) * p.hw_pad + q] = v;
+                const int c = cq * 128 + lane * 4;
+                if (p.out_hwc && q < p.hw) {
+                    uint2 o;
+                    o.x = pack_half2(acc.x, acc.y); o.y = pack_half2(acc.z, acc.w);
+                    *reinterpret_cast<uint2*>(p.out_hwc + ((size_t)(p.obj_begin + obj) * p.hw + q) * XM_CV + c) = o;
+                }
+                if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + ((size_t)obj * p.hw_pad + q) * XM_CV + c) = acc;
+            }
+            // (2) reference layout [object][channel][query] (tests, drop-in callers): 32 x 32 tiles transposed through smem
+            if (p.out_chw) {
+                float* tr = reinterpret_cast<float*>(&rd.v[0][0]) + (size_t)ww * 32 * 33;
+                const int qblocks = p.hw_pad / 32;
+                const int tiles = p.n_obj * qblocks * 16;
+                for (int t = cta * NWORK + ww; t < tiles; t += G * NWORK) {
+                    const int obj = t / (qblocks * 16);
+                    const int rem = t - obj * qblocks * 16;
+                    const int qb = rem >> 4, cb = rem & 15;
+                    const int q0 = qb * 32, c0 = cb * 32;
+                    const int rpair = q0 / QPAIR, ql0 = q0 - rpair * QPAIR;
+                    const int chalf = cb >> 3;
+                    const int row = ((rpair * p.n_obj + obj) << 1) | chalf;
+                    int item0, nsl;
+                    if (p.n_rows <= MAX_ROWS_TABLE) { item0 = cm.row_item0[row]; nsl = p.row_slices[row]; } else { item0 = row; nsl = 1; }
+                    const float* src = p.partial + (size_t)item0 * (QPAIR * 256) + (size_t)ql0 * 256 + (c0 & 255) + lane;
+                    float acc[32];
+#pragma unroll
+                    for (int qq = 0; qq < 32; ++qq) acc[qq] = 0.f;
+                    for (int sl = 0; sl < nsl; ++sl) {
+#pragma unroll
+                        for (int qq = 0; qq < 32; ++qq) acc[qq] += __ldcg(src + (size_t)sl * (QPAIR * 256) + qq * 256);
                     }
+#pragma unroll
+                    for (int qq = 0; qq < 32; ++qq) tr[qq * 33 + lane] = acc[qq];
+                    __syncwarp();
+                    const int q = q0 + lane;
+                    if (q < p.hw) {
+#pragma unroll 4
+                        for (int cc = 0; cc < 32; ++cc)
+                            p.out_chw[((size_t)(p.obj_begin + obj) * XM_CV + c0 + cc) * p.hw + q] = __float2half_rn(tr[lane * 33 + cc]);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
+            }
+        }
+        // (3) usage: use_count[column] += sum over the queries of the affinity (memory_util.py:62-63, kv_memory_store.py:96-103)
+        if (want_usage) {
+            const int ncol = sg.t64[sg.nseg] * TK;
+            for (int lin = cta * NTHREADS + threadIdx.x; lin < ncol; lin += G * NTHREADS) {
+                const unsigned long long u = __ldcg(p.uacc + lin);
+                if (u == 0ull) continue;
+                int sgi, col;
+                unlinear_col(sg, lin, sgi, col);
+                if (sg.usage[sgi] && col >= sg.begin[sgi] && col < sg.end[sgi]) sg.usage[sgi][col] += __ull2float_rn(u) * 9.094947017729282e-13f;   // 2^-40
             }
         }
     } else {
@@ -905,6 +1131,7 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
     // ------------------------------------------------------------------ teardown: last CTA out re-arms the counters
     tc_fence_before();
     __syncthreads();
+    K1_STAMP(10);
     if (warp == 1) tmem_dealloc(tmem, 512);
     if (threadIdx.x == 0) {
         __threadfence();
@@ -961,7 +1188,7 @@ __global__ void k1_topk_merge(const float* __restrict__ cand, int nlists, int hw
     if (lane == 0) tau[q] = kth;
 }
 
-// fp32 [n_obj][512][hw_pad] -> fp16 CHW / NHWC (T-shard, after the all-reduce)
+// fp32 [n_obj][hw_pad][512] -> fp16 CHW / NHWC (T-shard, after the all-reduce)
 __global__ void k1_cast(const float* __restrict__ src, int n_obj, int hw, int hw_pad, __half* __restrict__ out_chw, __half* __restrict__ out_hwc) {
     pdl_wait();
     pdl_launch_dependents();
@@ -970,16 +1197,16 @@ __global__ void k1_cast(const float* __restrict__ src, int n_obj, int hw, int hw
     const int c0 = blockIdx.y * 32, q0 = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;       // 32 x 8
     for (int r = ty; r < 32; r += 8) {
-        const int c = c0 + r, q = q0 + tx;
-        const float acc = (q < hw) ? src[((size_t)o * XM_CV + c) * hw_pad + q] : 0.f;
+        const int q = q0 + r, c = c0 + tx;
+        const float acc = (q < hw) ? src[((size_t)o * hw_pad + q) * XM_CV + c] : 0.f;
         tile[r][tx] = acc;
-        if (out_chw && q < hw) out_chw[((size_t)o * XM_CV + c) * hw + q] = __float2half_rn(acc);
+        if (out_hwc && q < hw) out_hwc[((size_t)o * hw + q) * XM_CV + c] = __float2half_rn(acc);
     }
-    if (out_hwc) {
+    if (out_chw) {
         __syncthreads();
         for (int r = ty; r < 32; r += 8) {
-            const int q = q0 + r, c = c0 + tx;
-            if (q < hw) out_hwc[((size_t)o * hw + q) * XM_CV + c] = __float2half_rn(tile[tx][r]);
+            const int c = c0 + r, q = q0 + tx;
+            if (q < hw) out_chw[((size_t)o * XM_CV + c) * hw + q] = __float2half_rn(tile[tx][r]);
         }
     }
 }
@@ -1035,11 +1262,13 @@ K1Geom k1_geom(int hw) {
     if (g.nslice1 > MAX_SLICE1) g.nslice1 = MAX_SLICE1;
     return g;
 }
+constexpr int K1_DEFAULT_COLUMNS = 1 << 20;      // memory columns the default workspace size can account usage for
 struct K1Ws {
-    K1Seg* plan; unsigned* ctr; float* candA; float* tau_lo; uint2* lists; int* lcnt; uint2* fin; float* partial;
+    K1Seg* plan; unsigned* ctr; unsigned long long* timeline; float* candA; float* tau_lo; uint2* lists; int* lcnt; uint2* fin; float* partial;
+    unsigned long long* uacc; size_t uacc_cols;
     size_t total;
 };
-K1Ws k1_carve(void* workspace, int hw, int n_obj_total) {
+K1Ws k1_carve(void* workspace, int hw, int n_obj_total, int64_t workspace_bytes = -1) {
     const K1Geom g = k1_geom(hw);
     uint8_t* ws = (uint8_t*)workspace;
     size_t off = 0;
@@ -1047,15 +1276,20 @@ K1Ws k1_carve(void* workspace, int hw, int n_obj_total) {
     auto take = [&](size_t bytes) { uint8_t* ptr = ws ? ws + off : nullptr; off += align_up(bytes, 256); return ptr; };
     w.plan = (K1Seg*)take(K1_PLAN_BYTES);
     w.ctr = (unsigned*)take(NCTR * 4);
+    w.timeline = (unsigned long long*)take((size_t)g.grid * 16 * 8 + 4 * 1024 * 8);       // stamps + diagnostics
     w.candA = (float*)take((size_t)g.qrows * g.nslice1 * 32 * 4);
     w.tau_lo = (float*)take((size_t)g.qrows * 4);
-    w.lists = (uint2*)take((size_t)g.qrows * g.nslice1 * LCAP * 8);
-    w.lcnt = (int*)take((size_t)g.qrows * g.nslice1 * 4);
+    w.lists = (uint2*)take((size_t)g.qrows * g.nslice1 * 2 * LCAP * 8);
+    w.lcnt = (int*)take((size_t)g.qrows * g.nslice1 * 2 * 4);
     w.fin = (uint2*)take((size_t)g.qrows * LISTK * 8);
     const size_t rows_max = (size_t)g.qpairs * (n_obj_total > 0 ? n_obj_total : 1) * 2;
     const size_t items_max = rows_max > (size_t)g.grid ? rows_max : (size_t)g.grid;
     w.partial = (float*)take(items_max * QPAIR * 256 * 4);
-    w.total = off;
+    // usage accumulator: one 8-byte cell per (64-padded) memory column; everything the caller provides beyond the fixed part
+    // (xm_affinity_workspace_bytes reserves room for K1_DEFAULT_COLUMNS columns)
+    w.uacc = (unsigned long long*)(ws ? ws + off : nullptr);
+    w.uacc_cols = workspace_bytes < 0 ? (size_t)K1_DEFAULT_COLUMNS : (workspace_bytes > (int64_t)off ? (size_t)(workspace_bytes - (int64_t)off) / 8 : 0);
+    w.total = off + (size_t)K1_DEFAULT_COLUMNS * 8;
     return w;
 }
 }  // namespace
@@ -1181,6 +1415,12 @@ int k1_launch(const xm_affinity_args_t* a, const K1Maps& maps, const K1Ws& w, in
     const K1Geom g = k1_geom(a->hw);
     const xm_group_t& gr = a->groups[group];
     XM_REQUIRE(g.qpairs + 8 <= NCTR && g.qpairs <= g.grid, "xm_affinity: hw = %d needs more query pairs (%d) than CTAs (%d)", a->hw, g.qpairs, g.grid);
+    {
+        int64_t cols = 0;
+        for (int i = 0; i < 3; ++i) if (a->banks[i].keys && a->banks[i].size > 0) cols += a->banks[i].cap + 64;
+        XM_REQUIRE((int64_t)w.uacc_cols >= cols, "xm_affinity: workspace accounts usage for %lld memory columns, the banks hold up to %lld "
+                   "(allocate xm_affinity_workspace_bytes() + 8 bytes per extra column)", (long long)w.uacc_cols, (long long)cols);
+    }
     K1Params p;
     memset(&p, 0, sizeof(p));
     p.seg = w.plan + group; p.bsq = a->bsq;
@@ -1189,8 +1429,10 @@ int k1_launch(const xm_affinity_args_t* a, const K1Maps& maps, const K1Ws& w, in
     p.do_usage = (group == 0) ? 1 : 0;
     p.mode = mode;
     p.qtiles = g.qtiles; p.qpairs = g.qpairs; p.nslice1 = g.nslice1;
+    p.a_stride = a->debug_scores ? 1 : 2;        // the test dump wants every score
     k1_plan_items(g, gr.n_obj, p);
-    p.ctr = w.ctr; p.candA = w.candA; p.tau_lo = w.tau_lo; p.lists = w.lists; p.lcnt = w.lcnt; p.fin = w.fin; p.partial = w.partial;
+    p.uacc = w.uacc; p.uacc_cols = (int)(w.uacc_cols > 0x7fffffff ? 0x7fffffff : w.uacc_cols);
+    p.ctr = w.ctr; p.timeline = w.timeline; p.candA = w.candA; p.tau_lo = w.tau_lo; p.lists = w.lists; p.lcnt = w.lcnt; p.fin = w.fin; p.partial = w.partial;
     p.tau_ext = tau_ext; p.inv_ext = inv_ext; p.top32_out = top32_out; p.out_f32 = out_f32;
     p.out_chw = write_fp16 ? (__half*)a->readout_chw : nullptr;
     p.out_hwc = write_fp16 ? (__half*)a->readout_hwc : nullptr;
@@ -1223,7 +1465,7 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
     int rc = k1_common_checks(a, "xm_affinity_readout");
     if (rc != XM_OK) return rc;
     XM_REQUIRE(a->readout_chw || a->readout_hwc, "xm_affinity_readout: no output buffer");
-    const K1Ws w = k1_carve(a->workspace, a->hw, a->n_obj_total);
+    const K1Ws w = k1_carve(a->workspace, a->hw, a->n_obj_total, a->workspace_bytes);
     if (!a->plan_is_resident) {
         // eager convenience path: build the table here and copy it (pageable source: staged before the call returns)
         K1Seg plan[XM_MAX_GROUPS];
@@ -1244,11 +1486,41 @@ extern "C" int xm_affinity_readout(const xm_affinity_args_t* a, void* stream_) {
     return XM_OK;
 }
 
+// diagnostics: copy the phase-boundary time stamps of the LAST launch on this workspace ([grid][16] uint64 ns) to the host
+extern "C" int xm_affinity_debug_timeline(void* workspace, int32_t hw, int32_t n_obj_total, unsigned long long* host_out, int32_t max_ctas) {
+    XM_REQUIRE(workspace && host_out, "xm_affinity_debug_timeline: null pointer");
+    const K1Ws w = k1_carve(workspace, hw, n_obj_total);
+    const int n = k1_geom(hw).grid < max_ctas ? k1_geom(hw).grid : max_ctas;
+    XM_CHECK_CUDA(cudaMemcpy(host_out, w.timeline, (size_t)n * 16 * 8, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+// diagnostics: candidates collected per query by the last sweep B on this workspace (sum of the thread lists' counts)
+extern "C" int xm_affinity_debug_counts(void* workspace, int32_t hw, int32_t n_obj_total, int32_t* host_out) {
+    const K1Ws w = k1_carve(workspace, hw, n_obj_total);
+    const K1Geom g = k1_geom(hw);
+    const int nl = 2 * g.nslice1;
+    int* tmp = (int*)malloc((size_t)g.qrows * nl * 4);
+    if (!tmp) return -1;
+    cudaError_t e = cudaMemcpy(tmp, w.lcnt, (size_t)g.qrows * nl * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) for (int q = 0; q < hw; ++q) { int t = 0; for (int l = 0; l < nl; ++l) t += tmp[(size_t)q * nl + l]; host_out[q] = t; }
+    free(tmp);
+    return e == cudaSuccess ? 0 : -2;
+}
+
+extern "C" int xm_affinity_debug_trace(void* workspace, int32_t hw, int32_t n_obj_total, unsigned long long* host_out) {
+    const K1Ws w = k1_carve(workspace, hw, n_obj_total);
+    XM_CHECK_CUDA(cudaMemcpy(host_out, w.timeline + 148 * 16, 4 * 1024 * 8, cudaMemcpyDeviceToHost));
+    XM_CHECK_CUDA(cudaMemset(w.timeline + 148 * 16, 0, 4 * 1024 * 8));
+    return 0;
+}
+
 // One-time zeroing of the barrier counters of a fresh workspace (the kernel re-arms them itself on exit).
 extern "C" int xm_affinity_workspace_init(void* workspace, int64_t workspace_bytes, int32_t hw, int32_t n_obj_total, void* stream) {
     XM_REQUIRE(workspace && workspace_bytes >= xm_affinity_workspace_bytes(hw, n_obj_total), "xm_affinity_workspace_init: workspace too small");
     const K1Ws w = k1_carve(workspace, hw, n_obj_total);
     XM_CHECK_CUDA(cudaMemsetAsync(w.ctr, 0, NCTR * 4, (cudaStream_t)stream));
+    XM_CHECK_CUDA(cudaMemsetAsync(w.timeline, 0, (size_t)k1_geom(hw).grid * 16 * 8 + 4 * 1024 * 8, (cudaStream_t)stream));
     return XM_OK;
 }
 
@@ -1267,7 +1539,7 @@ static int tshard_setup(const xm_affinity_args_t* a, cudaStream_t stream, K1Maps
     int rc = k1_common_checks(a, "xm_affinity_tshard");
     if (rc != XM_OK) return rc;
     XM_REQUIRE(a->n_groups == 1, "xm_affinity_tshard: exactly one object group per call");
-    w = k1_carve(a->workspace, a->hw, a->n_obj_total);
+    w = k1_carve(a->workspace, a->hw, a->n_obj_total, a->workspace_bytes);
     if (upload_plan) {
         K1Seg plan[XM_MAX_GROUPS];
         memset(plan, 0, sizeof(plan));

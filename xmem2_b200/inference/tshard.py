@@ -5,7 +5,7 @@ same query, and the exact global top-k softmax readout is assembled with three s
     stage_a (local slot maxima -> lower bound)          all_reduce(MAX)   tau_lo      [hw_pad]            fp32
     stage_b (local scores > pred(tau_lo) -> 32 largest) all_gather        top32       [R][hw_pad][32]     fp32
     merge   (exact tau, 1/den; identical on every rank)
-    stage_c (local P.V with the global normalisers)     all_reduce(SUM)   readout_f32 [n_obj][512][hw_pad] fp32
+    stage_c (local P.V with the global normalisers)     all_reduce(SUM)   readout_f32 [n_obj][hw_pad][512] fp32
 
 No max/sum all-reduce of a softmax is needed: the top-k branch of the reference has no max subtraction
 (model/memory_util.py:48-49), so the gathered candidate scores determine both the threshold and the denominator.
@@ -60,7 +60,7 @@ class ShardedReader:
                 gathered=torch.empty((self.world, hw_pad, 32), dtype=torch.float32, device=device),
                 tau=torch.empty(hw_pad, dtype=torch.float32, device=device),
                 inv_den=torch.empty(hw_pad, dtype=torch.float32, device=device),
-                acc=torch.empty((n_obj, lib.CV, hw_pad), dtype=torch.float32, device=device))
+                acc=torch.empty((n_obj, hw_pad, lib.CV), dtype=torch.float32, device=device))
         return self._bufs[key]
 
     def read(self, args: "lib.XmAffinityArgs", out_hwc: torch.Tensor):
