@@ -33,6 +33,9 @@ class Stats:
         self.mean_dprob = 0.0
         self.frames = 0
         self.per_frame = []          # (frame, argmax mismatch fraction, largest oracle margin among the mismatches)
+        self.mismatch_unsat = 0      # disagreements on pixels whose oracle top-2 classes are both away from the 1e-7 clamp
+        self.pixels_unsat = 0
+        self.eps_unsat = 0.0
 
     def add(self, p, po):
         d, do = _log_odds(p), _log_odds(po)
@@ -47,8 +50,15 @@ class Stats:
         bad = am != amo
         self.mismatch += int(bad.sum()); self.pixels += bad.numel()
         eps_f = 0.0
+        lpo = po.float().clamp_min(1e-30).log()
+        top2 = lpo.topk(2, dim=0).values
+        # "unsaturated": neither of the oracle's two most likely classes sits at the 1e-7 clamp of aggregate() (aggregate.py:10),
+        # where probabilities are quantised to multiples of 6e-8 and margins of ln 2 / ln 3 are float artefacts
+        unsat_px = (top2[0] < -1e-5) & (top2[1] > -13.0)
+        self.pixels_unsat += int(unsat_px.sum()); self.mismatch_unsat += int((bad & unsat_px).sum())
+        if (bad & unsat_px).any():
+            self.eps_unsat = max(self.eps_unsat, (top2[0] - top2[1])[bad & unsat_px].max().item())
         if bad.any():
-            top2 = po.float().clamp_min(1e-30).log().topk(2, dim=0).values
             eps_f = (top2[0] - top2[1])[bad].max().item()
             self.eps = max(self.eps, eps_f)
         self.per_frame.append((self.frames, round(float(bad.float().mean()), 6), round(eps_f, 4)))
@@ -58,6 +68,8 @@ class Stats:
     def as_dict(self):
         return dict(dlogit_p50=self.p50, dlogit_p99=self.p99, dlogit_max=self.max, argmax_mismatch_frac=self.mismatch / max(1, self.pixels),
                     argmax_eps=self.eps, mean_dprob=self.mean_dprob, frames=self.frames,
+                    argmax_mismatch_unsat_frac=self.mismatch_unsat / max(1, self.pixels_unsat), argmax_eps_unsat=self.eps_unsat,
+                    unsat_pixel_frac=self.pixels_unsat / max(1, self.pixels),
                     worst_frames=sorted(self.per_frame, key=lambda t: -t[1])[:8])
 
 

@@ -454,37 +454,23 @@ struct ScanCtx {
     ptrdiff_t dbg_stride;
 };
 
-// a thread whose list is (nearly) full: per-score appends with the replace-min rule (exact top-LCAP of the thread's columns).
-// Everything by value: taking the address of the caller's score registers would move them to local memory.
-struct SlowRet { int cnt; float thr; };
-__device__ __noinline__ SlowRet scan_block_slow(uint2* glist, int cnt, float thr, int lin, float s0, float s1, float s2, float s3, float s4,
-                                                float s5, float s6, float s7, float s8, float s9, float s10, float s11, float s12, float s13,
-                                                float s14, float s15) {
-    const float sc[16] = {s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15};
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-        if (sc[j] > thr) list_append(glist, cnt, thr, sc[j], lin + j);
-    SlowRet r; r.cnt = cnt; r.thr = thr;
-    return r;
-}
-
 template <int SWEEP, bool FULL, bool DBG>
 __device__ __forceinline__ void scan_block16(const uint32_t (&r)[16], const float* msp, int c, float (&slot)[NSLOT], ScanCtx& cx) {
-    float sc[16];
-#pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-        const float4 f = *reinterpret_cast<const float4*>(msp + c * 16 + j);
-        sc[j] = score2(r[j], cx.bsq8, f.x); sc[j + 1] = score2(r[j + 1], cx.bsq8, f.y);
-        sc[j + 2] = score2(r[j + 2], cx.bsq8, f.z); sc[j + 3] = score2(r[j + 3], cx.bsq8, f.w);
-    }
-    if (!FULL) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int n = c * 16 + j;
-            sc[j] = (n >= cx.lo && n < cx.hi) ? sc[j] : -INFINITY;
-        }
-    }
     if (SWEEP == 0) {
+        float sc[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const float4 f = *reinterpret_cast<const float4*>(msp + c * 16 + j);
+            sc[j] = score2(r[j], cx.bsq8, f.x); sc[j + 1] = score2(r[j + 1], cx.bsq8, f.y);
+            sc[j + 2] = score2(r[j + 2], cx.bsq8, f.z); sc[j + 3] = score2(r[j + 3], cx.bsq8, f.w);
+        }
+        if (!FULL) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = c * 16 + j;
+                sc[j] = (n >= cx.lo && n < cx.hi) ? sc[j] : -INFINITY;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) slot[j] = fmax3(slot[j], sc[j], sc[j + 8]);      // 8 slots, one FMNMX3 per two scores
         if (DBG) {
@@ -492,40 +478,42 @@ __device__ __forceinline__ void scan_block16(const uint32_t (&r)[16], const floa
             for (int j = 0; j < 16; ++j) if (sc[j] != -INFINITY) cx.dbg[(ptrdiff_t)(c * 16 + j) * cx.dbg_stride] = sc[j];
         }
     } else {
-        // maxima of the four 4-column groups (FMNMX3), then of the block; the append code below only runs for the groups in
-        // which some lane of the warp is above its threshold (~20 % of them), and is branch-free (predicated store + add)
-        const float g0 = fmaxf(fmax3(sc[0], sc[1], sc[2]), sc[3]), g1 = fmaxf(fmax3(sc[4], sc[5], sc[6]), sc[7]);
-        const float g2 = fmaxf(fmax3(sc[8], sc[9], sc[10]), sc[11]), g3 = fmaxf(fmax3(sc[12], sc[13], sc[14]), sc[15]);
-        const float m = fmaxf(fmax3(g0, g1, g2), g3);
-        if (__any_sync(0xffffffffu, m > cx.thr)) {
-            const int lin = cx.lin0 + c * 16;
-            // warp-uniform votes first (the per-lane branch on the list fill below must not contain warp collectives)
-            const bool v0 = __any_sync(0xffffffffu, g0 > cx.thr), v1 = __any_sync(0xffffffffu, g1 > cx.thr);
-            const bool v2 = __any_sync(0xffffffffu, g2 > cx.thr), v3 = __any_sync(0xffffffffu, g3 > cx.thr);
-            if (cx.cnt <= LCAP - 16) {
+        // 3 instructions per score: t = acc/8 - bsq8, d = thr - t*ms (ONE fma, exact product), sign bit of d shifted into a mask.
+        // sign(d) is set whenever the exact product exceeds thr -- a superset of fl(t*ms) > thr -- so the flagged scores are
+        // recomputed with the reference expression (score2) and compared again before they are listed.
+        uint32_t mask = 0u;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const bool vg = g == 0 ? v0 : (g == 1 ? v1 : (g == 2 ? v2 : v3));
-                    if (vg) {
+        for (int j = 0; j < 16; j += 4) {
+            const float4 f = *reinterpret_cast<const float4*>(msp + c * 16 + j);
+            const float ms[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-                        for (int j = 4 * g; j < 4 * g + 4; ++j) {
-                            asm volatile(
-                                "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
-                                "setp.gt.f32 p, %1, %2;\n\t"
-                                "mad.wide.s32 a, %0, 8, %3;\n\t"
-                                "@p st.global.cg.v2.b32 [a], {%4, %5};\n\t"
-                                "@p add.s32 %0, %0, 1;\n\t}"
-                                : "+r"(cx.cnt)
-                                : "f"(sc[j]), "f"(cx.thr), "l"(cx.glist), "r"(__float_as_uint(sc[j])), "r"(lin + j)
-                                : "memory");
-                        }
-                    }
-                }
-            } else if (m > cx.thr) {
-                const SlowRet r = scan_block_slow(cx.glist, cx.cnt, cx.thr, lin, sc[0], sc[1], sc[2], sc[3], sc[4], sc[5], sc[6], sc[7], sc[8],
-                                                  sc[9], sc[10], sc[11], sc[12], sc[13], sc[14], sc[15]);
-                cx.cnt = r.cnt; cx.thr = r.thr;
+            for (int u = 0; u < 4; ++u) {
+                const float t = fmaf(__uint_as_float(r[j + u]), 0.125f, -cx.bsq8);
+                const float d = fmaf(-t, ms[u], cx.thr);
+                mask = __funnelshift_l(__float_as_uint(d), mask, 1);       // score j ends up at bit 15 - j
             }
+        }
+        if (!FULL) {
+            const int jlo = max(0, cx.lo - c * 16), jhi = min(16, cx.hi - c * 16);     // valid j in [jlo, jhi)
+            const uint32_t valid = (jhi > jlo) ? (((1u << (jhi - jlo)) - 1u) << (16 - jhi)) : 0u;
+            mask &= valid;
+        }
+        if (mask) {                                                         // ~4 % of the lanes
+            const int lin = cx.lin0 + c * 16;
+            do {
+                const int bit = 31 - __clz(mask);
+                mask &= ~(1u << bit);
+                const int j = 15 - bit;
+                // r[j] with a dynamic j: binary select tree (registers cannot be indexed)
+                const bool b0 = j & 1, b1 = j & 2, b2 = j & 4, b3 = j & 8;
+                const uint32_t x0 = b0 ? r[1] : r[0], x1 = b0 ? r[3] : r[2], x2 = b0 ? r[5] : r[4], x3 = b0 ? r[7] : r[6];
+                const uint32_t x4 = b0 ? r[9] : r[8], x5 = b0 ? r[11] : r[10], x6 = b0 ? r[13] : r[12], x7 = b0 ? r[15] : r[14];
+                const uint32_t y0 = b1 ? x1 : x0, y1 = b1 ? x3 : x2, y2 = b1 ? x5 : x4, y3 = b1 ? x7 : x6;
+                const uint32_t z0 = b2 ? y1 : y0, z1 = b2 ? y3 : y2;
+                const uint32_t acc = b3 ? z1 : z0;
+                const float v = score2(acc, cx.bsq8, msp[c * 16 + j]);
+                if (v > cx.thr) list_append(cx.glist, cx.cnt, cx.thr, v, lin + j);
+            } while (mask);
         }
         __syncwarp();
     }
@@ -1045,74 +1033,86 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
         }
 
         // ---------------------------------------------------------------- reduce the column-slice partials
+        // One work item per CTA (the usual case): the CTAs of a ROW synchronise among themselves and share that row's
+        // reduction, so rows that finish early do not wait for the slowest CTA of the grid.  Otherwise: grid barrier.
         __syncthreads();
         K1_STAMP(8);
-        cta_group_barrier(p.ctr, ++grid_uses * G, 44);
+        const bool row_sync = p.n_items <= G && p.n_rows <= MAX_ROWS_TABLE;
+        int my_row = 0, my_sl = 0, my_nsl = 1;
+        if (row_sync) {
+            if (cta < p.n_items) {
+                while (cm.row_item0[my_row + 1] <= cta) ++my_row;
+                my_sl = cta - cm.row_item0[my_row]; my_nsl = p.row_slices[my_row];
+                cta_group_barrier(p.ctr + 96 + my_row, my_nsl, 44);
+            }
+        } else {
+            cta_group_barrier(p.ctr, ++grid_uses * G, 44);
+        }
         K1_STAMP(9);
-        if (warp >= 2) {
-            // (1) NHWC outputs: one warp per (object, query, 128-channel quarter), a lane sums 4 channels over the slices
-            //     (independent 16-byte loads, 512 contiguous bytes per warp and slice)
-            const int units = p.n_obj * p.hw_pad * 4;
-            for (int u = cta * NWORK + ww; u < units; u += G * NWORK) {
-                const int obj = u / (p.hw_pad * 4);
-                const int rem = u - obj * p.hw_pad * 4;
-                const int q = rem >> 2, cq = rem & 3;
-                const int rpair = q / QPAIR, ql = q - rpair * QPAIR;
-                const int chalf = cq >> 1;
-                const int row = ((rpair * p.n_obj + obj) << 1) | chalf;
+        if (warp >= 2 && (!row_sync || cta < p.n_items)) {
+            auto reduce_row = [&](int row, int v0, int vstride) {
+                const int chalf = row & 1;
+                const int obj = (row >> 1) % p.n_obj;
+                const int rpair = (row >> 1) / p.n_obj;
+                const int rnqh = (rpair * 2 + 1 < p.qtiles) ? 2 : 1;
                 int item0, nsl;
                 if (p.n_rows <= MAX_ROWS_TABLE) { item0 = cm.row_item0[row]; nsl = p.row_slices[row]; } else { item0 = row; nsl = 1; }
-                const float4* src = reinterpret_cast<const float4*>(p.partial + (size_t)item0 * (QPAIR * 256) + (size_t)ql * 256 + (cq & 1) * 128) + lane;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float* pbase = p.partial + (size_t)item0 * (QPAIR * 256);
+                // (1) NHWC outputs: one warp per (query, 128-channel quarter), a lane sums 4 channels over the slices
+                //     (independent 16-byte loads, 512 contiguous bytes per warp and slice)
+                for (int v = v0; v < rnqh * TQ * 2; v += vstride) {
+                    const int ql = v >> 1, cq = chalf * 2 + (v & 1);
+                    const int q = rpair * QPAIR + ql;
+                    const float4* src = reinterpret_cast<const float4*>(pbase + (size_t)ql * 256 + (v & 1) * 128) + lane;
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-                for (int s = 0; s < nsl; ++s) {
-                    const float4 f = __ldcg(src + (size_t)s * (QPAIR * 256 / 4));
-                    acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
-                }
-                const int c = cq * 128 + lane * 4;
-                if (p.out_hwc && q < p.hw) {
-                    uint2 o;
-                    o.x = pack_half2(acc.x, acc.y); o.y = pack_half2(acc.z, acc.w);
-                    *reinterpret_cast<uint2*>(p.out_hwc + ((size_t)(p.obj_begin + obj) * p.hw + q) * XM_CV + c) = o;
-                }
-                if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + ((size_t)obj * p.hw_pad + q) * XM_CV + c) = acc;
-            }
-            // (2) reference layout [object][channel][query] (tests, drop-in callers): 32 x 32 tiles transposed through smem
-            if (p.out_chw) {
-                float* tr = reinterpret_cast<float*>(&rd.v[0][0]) + (size_t)ww * 32 * 33;
-                const int qblocks = p.hw_pad / 32;
-                const int tiles = p.n_obj * qblocks * 16;
-                for (int t = cta * NWORK + ww; t < tiles; t += G * NWORK) {
-                    const int obj = t / (qblocks * 16);
-                    const int rem = t - obj * qblocks * 16;
-                    const int qb = rem >> 4, cb = rem & 15;
-                    const int q0 = qb * 32, c0 = cb * 32;
-                    const int rpair = q0 / QPAIR, ql0 = q0 - rpair * QPAIR;
-                    const int chalf = cb >> 3;
-                    const int row = ((rpair * p.n_obj + obj) << 1) | chalf;
-                    int item0, nsl;
-                    if (p.n_rows <= MAX_ROWS_TABLE) { item0 = cm.row_item0[row]; nsl = p.row_slices[row]; } else { item0 = row; nsl = 1; }
-                    const float* src = p.partial + (size_t)item0 * (QPAIR * 256) + (size_t)ql0 * 256 + (c0 & 255) + lane;
-                    float acc[32];
-#pragma unroll
-                    for (int qq = 0; qq < 32; ++qq) acc[qq] = 0.f;
-                    for (int sl = 0; sl < nsl; ++sl) {
-#pragma unroll
-                        for (int qq = 0; qq < 32; ++qq) acc[qq] += __ldcg(src + (size_t)sl * (QPAIR * 256) + qq * 256);
+                    for (int s = 0; s < nsl; ++s) {
+                        const float4 f = __ldcg(src + (size_t)s * (QPAIR * 256 / 4));
+                        acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
                     }
+                    const int c = cq * 128 + lane * 4;
+                    if (p.out_hwc && q < p.hw) {
+                        uint2 o;
+                        o.x = pack_half2(acc.x, acc.y); o.y = pack_half2(acc.z, acc.w);
+                        *reinterpret_cast<uint2*>(p.out_hwc + ((size_t)(p.obj_begin + obj) * p.hw + q) * XM_CV + c) = o;
+                    }
+                    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + ((size_t)obj * p.hw_pad + q) * XM_CV + c) = acc;
+                }
+                // (2) reference layout [object][channel][query] (tests, drop-in callers): 32 x 32 tiles transposed through smem
+                if (p.out_chw) {
+                    float* tr = reinterpret_cast<float*>(&rd.v[0][0]) + (size_t)ww * 32 * 33;
+                    for (int t = v0; t < rnqh * 4 * 8; t += vstride) {
+                        const int qb = t >> 3, cb = t & 7;
+                        const int ql0 = qb * 32, c0 = chalf * 256 + cb * 32;
+                        const int q0 = rpair * QPAIR + ql0;
+                        const float* src = pbase + (size_t)ql0 * 256 + cb * 32 + lane;
+                        float acc[32];
 #pragma unroll
-                    for (int qq = 0; qq < 32; ++qq) tr[qq * 33 + lane] = acc[qq];
-                    __syncwarp();
-                    const int q = q0 + lane;
-                    if (q < p.hw) {
+                        for (int qq = 0; qq < 32; ++qq) acc[qq] = 0.f;
+                        for (int sl = 0; sl < nsl; ++sl) {
+#pragma unroll
+                            for (int qq = 0; qq < 32; ++qq) acc[qq] += __ldcg(src + (size_t)sl * (QPAIR * 256) + qq * 256);
+                        }
+#pragma unroll
+                        for (int qq = 0; qq < 32; ++qq) tr[qq * 33 + lane] = acc[qq];
+                        __syncwarp();
+                        const int q = q0 + lane;
+                        if (q < p.hw) {
 #pragma unroll 4
-                        for (int cc = 0; cc < 32; ++cc)
-                            p.out_chw[((size_t)(p.obj_begin + obj) * XM_CV + c0 + cc) * p.hw + q] = __float2half_rn(tr[lane * 33 + cc]);
+                            for (int cc = 0; cc < 32; ++cc)
+                                p.out_chw[((size_t)(p.obj_begin + obj) * XM_CV + c0 + cc) * p.hw + q] = __float2half_rn(tr[lane * 33 + cc]);
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
+            };
+            if (row_sync) {
+                reduce_row(my_row, my_sl * NWORK + ww, my_nsl * NWORK);
+            } else {
+                for (int row = 0; row < p.n_rows; ++row) reduce_row(row, cta * NWORK + ww, G * NWORK);
             }
         }
+        if (want_usage && row_sync) cta_group_barrier(p.ctr, ++grid_uses * G, 45);     // every k-tile's column sums are complete
         // (3) usage: use_count[column] += sum over the queries of the affinity (memory_util.py:62-63, kv_memory_store.py:96-103)
         if (want_usage) {
             const int ncol = sg.t64[sg.nseg] * TK;
