@@ -178,6 +178,15 @@ int xm_upsample4x_aggregate(const void* logits4, int32_t n, int32_t h4, int32_t 
 /* value fp16 [n_obj][hw][512] (NHWC) -> arena fp16 [n_obj][512][cap] columns [col0, col0+hw)               */
 int xm_value_append(const void* value_hwc, int32_t n_obj, int32_t hw, void* arena, int64_t cap, int32_t col0, void* stream);
 
+/* ---------------------------------------------------------------- annotation-candidate selector */
+/* Cycle dissimilarity of ordered frame pairs (inference/frame_selection/frame_selection.py:213-221):
+ *   out[p] = mean over [hw, hw] of relu(S_ab - S_ba),  A = pair_a[p], B = pair_b[p], S as in model/memory_util.py:7-39.
+ * kp_all/qp_all fp16 [n_frames][hw_pad][128] (xm_key_pack / xm_query_pack rows), bsq_all/ms_all fp32 [n_frames][hw_pad];
+ * partial: scratch fp32 [n_pairs][(hw_pad/128)^2].  Deterministic (fixed summation order). */
+int xm_pair_dissimilarity(const void* kp_all, const void* qp_all, const float* bsq_all, const float* ms_all, int32_t n_frames,
+                          int32_t hw, int32_t hw_pad, const int32_t* pair_a, const int32_t* pair_b, int32_t n_pairs, float* partial,
+                          float* out, void* stream);
+
 /* ---------------------------------------------------------------- driver-side post-processing */
 /* prob fp32 [channels][in_h][in_w] with element strides (stride_c, stride_h, 1) -> out uint8 [out_h][out_w]:
  * bilinear resize (align_corners = False) + argmax over channels (first maximum) + optional 256-entry label table.

@@ -52,9 +52,10 @@ class Stats:
         eps_f = 0.0
         lpo = po.float().clamp_min(1e-30).log()
         top2 = lpo.topk(2, dim=0).values
-        # "unsaturated": neither of the oracle's two most likely classes sits at the 1e-7 clamp of aggregate() (aggregate.py:10),
-        # where probabilities are quantised to multiples of 6e-8 and margins of ln 2 / ln 3 are float artefacts
-        unsat_px = (top2[0] < -1e-5) & (top2[1] > -13.0)
+        # "saturated tie": the background probability has vanished (some object's sigmoid sits at the 1e-7 clamp of aggregate(),
+        # aggregate.py:10) but a second class still holds > 1e-3: two objects whose sigmoids are BOTH within a few fp32 ulps
+        # of 1.  Their odds are small integer multiples of 6e-8, so the "margins" ln 2 / ln 3 there are float artefacts.
+        unsat_px = ~((po[0].float() < 1e-6) & (top2[1] > -6.9))
         self.pixels_unsat += int(unsat_px.sum()); self.mismatch_unsat += int((bad & unsat_px).sum())
         if (bad & unsat_px).any():
             self.eps_unsat = max(self.eps_unsat, (top2[0] - top2[1])[bad & unsat_px].max().item())

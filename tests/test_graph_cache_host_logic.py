@@ -21,6 +21,8 @@ class _FakeMem:
     def __init__(self):
         self.h = torch.zeros(1, 1, 64, 2, 2)
         self.plans = 0
+        self._ws = object()          # every manager starts with its own K1 workspace
+        self.adopted = []
 
     def layout_signature(self):
         return ('layout',)
@@ -33,6 +35,10 @@ class _FakeMem:
 
     def upload_plan(self, hw, dev):
         self.plans += 1
+
+    def adopt_workspace(self, ws):
+        self._ws = ws
+        self.adopted.append(ws)
 
 
 class _FakeGraph:
@@ -49,7 +55,7 @@ def test_warmup_record_replay_and_cross_core_reuse(monkeypatch):
     def fake_capture(self, image, mem_frame):
         captures.append(mem_frame)
         return {'image': image.clone(), 'owner': [None], 'hidden': torch.zeros(1, 1, 64, 2, 2), 'graph': _FakeGraph(),
-                'launches': 3, 'prob': torch.zeros(2, 4, 4)}
+                'launches': 3, 'prob': torch.zeros(2, 4, 4), 'ws': self.memory._ws}
 
     monkeypatch.setattr(ic.InferenceCore, '_capture', fake_capture)
     net = torch.nn.Linear(1, 1)
@@ -70,6 +76,8 @@ def test_warmup_record_replay_and_cross_core_reuse(monkeypatch):
     b = make_core()                                                  # next video on the same network
     assert b._graph_step(img, False) is not None and captures == [False, True]
     assert a.memory.get_hidden().data_ptr() != b.memory.get_hidden().data_ptr()   # previous user got its own copy
+    # the recorded kernels point into the FIRST core's K1 workspace: the inheriting core must adopt it
+    assert b.memory.adopted == [a.memory._ws] and b.memory._ws is a.memory._ws
     assert len(ic._graph_cache(net)) == 2
     other = torch.nn.Linear(1, 1)                                    # a different network never sees these graphs
     assert ic._graph_cache(other) == {}

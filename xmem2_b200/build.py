@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libxmem2_b200.so')
-SOURCES = ['common.cu', 'k1_affinity.cu', 'conv_igemm.cu', 'eltwise.cu', 'postproc.cu']
+SOURCES = ['common.cu', 'k1_affinity.cu', 'conv_igemm.cu', 'conv_igemm_pair.cu', 'pair_dissim.cu', 'eltwise.cu', 'postproc.cu']
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math',
          '-Xcompiler', '-fPIC', '-cudart', 'static'] + os.environ.get('XMEM_EXTRA_NVCC_FLAGS', '').split()
 
@@ -48,39 +48,5 @@ def build(force=False, verbose=False):
     return OUT
 
 
-EXP_OUT = os.path.join(HERE, 'libxmem2_b200_exp.so')
-EXP_SOURCES = ['conv_igemm_csk.cu', 'conv_igemm_2cta.cu', 'conv_igemm_mc.cu', 'conv_igemm_halo.cu', 'pair_dissim.cu']
-
-
-def build_experimental(force=False):
-    """libxmem2_b200_exp.so: the round-2 head-start kernels of csrc/experimental/ (four `xm_conv2d_nhwc_<variant>` entry points and
-    `xm_pair_dissimilarity`) plus their own copy of common.cu.  NOT part of the product library and not
-    built by `build()`; `XMEM_CONV_IMPL=<variant>` makes `lib.conv2d_nhwc` call into it (see lib.py)."""
-    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))]
-    jobs = [(os.path.join(CSRC, 'common.cu'), os.path.join(HERE, 'build', 'exp_common.o'))]
-    jobs += [(os.path.join(CSRC, 'experimental', s), os.path.join(HERE, 'build', 'exp_' + s.replace('.cu', '.o'))) for s in EXP_SOURCES]
-    procs = []
-    for src, obj in jobs:
-        if force or _stale(obj, [src] + headers):
-            procs.append((src, subprocess.Popen([nvcc] + FLAGS + ['-c', src, '-o', obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    failed = False
-    for src, p in procs:
-        out, _ = p.communicate()
-        if out.strip():
-            print(f'--- {src}\n{out}')
-        failed |= p.returncode != 0
-    if failed:
-        raise RuntimeError('nvcc failed (experimental)')
-    objs = [o for _, o in jobs]
-    if force or procs or _stale(EXP_OUT, objs):
-        subprocess.check_call([nvcc, '-shared', '-cudart', 'static', '-o', EXP_OUT] + objs)
-    return EXP_OUT
-
-
 if __name__ == '__main__':
-    if '--experimental' in sys.argv:
-        print(build_experimental(force='--force' in sys.argv))
-    else:
-        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -37,3 +37,6 @@ struct XmPerDevice { unsigned long long done_mask; };       // zero-initialised 
 bool xm_first_use_on_device(XmPerDevice* token);             // true exactly once per (token, current device); thread-safe
 
 void xm_count_launches(int n);
+
+// CTA-pair (cta_group::2) convolution, conv_igemm_pair.cu; same contract as xm_conv2d_nhwc, cout_pad % 128 == 0 only
+int xm_conv2d_pair(const xm_conv_args_t* a, void* stream);

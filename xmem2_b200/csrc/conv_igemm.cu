@@ -1,3 +1,20 @@
+// conv_igemm.cu — implicit-GEMM convolution on tcgen05 for NHWC fp16 activations, with CLUSTER split-K.
+//
+// Small grids (the 30x54 layers cover 28-112 of the 148 SMs) are bound by what each SM can pull through TMA (~57 GB/s per
+// SM measured, tests/microbench/tma_ingest.cu), so the only way to go faster is to put more SMs on the layer: the S <= 3
+// CTAs that share an output tile (blockIdx.z = 0..S-1) form a thread-block cluster (1,1,S); every CTA accumulates its K
+// range in its own TMEM, the peers (rank > 0) push their fp32 accumulators into the leader's shared memory through DSMEM
+// (st.shared::cluster), and the leader adds them in rank order and runs the usual epilogue.  No global workspace, no atomics.
+// Protocol after the main loop (all 192 threads of every CTA execute both cluster barriers):
+//   epilogue warps wait `done` (their CTA's MMAs finished)  ->  cluster barrier #1: every CTA's stage buffers are free
+//   peers: TMEM -> registers -> leader's smem partial[rank-1] (layout [BN/4][128 rows] float4: conflict-free)
+//   cluster barrier #2 (release/acquire): partials visible to the leader; peers leave
+//   leader: own TMEM + partial[0] (+ partial[1]) -> bias / residual / ReLU -> TMA store (or the plain store path)
+// Layers that fill more than one wave of 128x128 tiles but fit one wave of CTA pairs go to conv_igemm_pair.cu
+// (cta_group::2, M = 256, each CTA loads half of the weight tile: half the bytes per FLOP through each SM's TMA).
+// Measured on B200 (round 2, tests/bench_conv.py): 905 -> 853 us per 480p frame against the round-1 kernel with its global
+// split-K; the pair kernel takes the 60x108 512->512 decoder convolution from 57 to 32 us.
+//
 // conv_igemm.cu — implicit-GEMM convolution on tcgen05 for NHWC fp16 activations.
 //
 // One kernel serves every 1x1 / 3x3 (stride 1 or 2, padding k/2) convolution on the XMem++ path
@@ -26,6 +43,20 @@ using namespace tc5;
 
 namespace {
 
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `local_smem_addr` in the shared memory of CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32x4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 struct alignas(64) ConvMaps {
     CUtensorMap a[3];
@@ -51,9 +82,7 @@ struct ConvP {
     __half* out;
     __half* out_relu;
     int out_stride, out_offset;
-    int splits, ksteps_per_split;     // split-K: blockIdx.z owns k-steps [z*kps, min((z+1)*kps, ksteps))
-    float* ws_partial;                // [tile][split][128][BN] fp32
-    int* ws_counter;                  // [tile] arrival counters (zero before and after every launch)
+    int splits, ksteps_per_split;     // cluster split-K: blockIdx.z (= cluster rank) owns k-steps [z*kps, min((z+1)*kps, ksteps))
     int tma_epilogue;                 // 1: stage the tile in swizzled smem, residual in / output out through TMA
 };
 
@@ -66,13 +95,12 @@ struct ConvSmem {
     uint64_t done;
     uint64_t resbar;
     uint32_t tmem_base;
-    int is_last;
     float bias[BN];
 };
 
 template <int BN, int CONV_STAGES>
 __global__ void __launch_bounds__(192)
-conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
+conv_igemm_csk_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
     extern __shared__ uint8_t smem_raw[];
     using Smem = ConvSmem<BN, CONV_STAGES>;
     Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -160,37 +188,40 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
             mma_commit(&sm.done);
         }
     } else {
-        const int lane_base = (warp & 3) * 32;
-        const int row = lane_base + lane;
-        const int yo = y0 + row / p.tw, xo = x0 + row % p.tw;
-        const bool pix_ok = (yo < p.Ho) && (xo < p.Wo);
-        const size_t pix = ((size_t)b * p.Ho + yo) * p.Wo + xo;
-        const size_t rpix = ((size_t)(p.residual_bcast ? 0 : b) * p.Ho + yo) * p.Wo + xo;
-        mbar_wait(&sm.done, 0, 23);
+        mbar_wait(&sm.done, 0, 23);        // this CTA's accumulator is complete, its stage buffers are idle
         tc_fence_after();
-        const int tile_lin = blockIdx.x * gridDim.y + blockIdx.y;
-        if (p.splits > 1) {
-            // write this split's fp32 partial tile, then the last CTA to arrive reduces all splits in fixed order
-            float* mine = p.ws_partial + (((size_t)tile_lin * p.splits + blockIdx.z) * 128 + row) * BN;
+    }
+    __syncwarp();                          // warps 0/1 re-converge before the aligned cluster barriers
+    // ---------------------------------------------------------------- cluster split-K fix-up
+    // partial[peer][BN/4][128] float4 in the LEADER's A ring, behind the (BN/64) TMA-store boxes
+    const uint32_t crank = (p.splits > 1) ? cluster_ctarank() : 0u;
+    uint8_t* const partial0 = &sm.a[0][0] + (BN / 64) * 128 * 128;
+    if (p.splits > 1) {
+        cluster_sync_all();                // #1: all MMAs of the cluster retired -> the leader's ring may be overwritten
+        if (warp >= 2 && crank > 0) {
+            const int lane_base = (warp & 3) * 32;
+            const int row = lane_base + lane;
+            const uint32_t dst0 = map_to_cta(smem_u32(partial0 + (size_t)(crank - 1) * 128 * BN * 4), 0);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(lane_base) << 16) + c0, r);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(mine + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                for (int j = 0; j < 32; j += 4)
+                    st_cluster_f32x4(dst0 + (uint32_t)(((c0 + j) / 4 * 128 + row) * 16), r[j], r[j + 1], r[j + 2], r[j + 3]);
             }
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 64) {
-                const int old = atomicAdd(p.ws_counter + tile_lin, 1);
-                sm.is_last = (old == p.splits - 1) ? 1 : 0;
-                if (old == p.splits - 1) p.ws_counter[tile_lin] = 0;      // ready for the next launch
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (!sm.is_last) goto teardown;
-            __threadfence();
         }
+        cluster_sync_all();                // #2: partials are visible in the leader's shared memory
+    }
+    if (warp >= 2 && crank == 0) {
+        const int lane_base = (warp & 3) * 32;
+        const int row = lane_base + lane;
+        const int yo = y0 + row / p.tw, xo = x0 + row % p.tw;
+        const bool pix_ok = (yo < p.Ho) && (xo < p.Wo);
+        const size_t pix = ((size_t)b * p.Ho + yo) * p.Wo + xo;
+        const size_t rpix = ((size_t)(p.residual_bcast ? 0 : b) * p.Ho + yo) * p.Wo + xo;
+        const int n_peers = p.splits - 1;
         if (p.tma_epilogue) {
             // Stage buffers are free now (every MMA has completed): a[] holds the output tile, b[] the residual tile,
             // both as 64-channel boxes of 128 pixel rows x 128 B with the 128-byte swizzle (conflict-free 16-B accesses).
@@ -208,23 +239,20 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
 #pragma unroll
                 for (int hlf = 0; hlf < 2; ++hlf) {
                     const int c0 = 64 * k + 32 * hlf;
-                    if (p.splits > 1) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[32 * hlf + j] = 0.f;
-                        for (int z = 0; z < p.splits; ++z) {
-                            const float* src = p.ws_partial + (((size_t)tile_lin * p.splits + z) * 128 + row) * BN + c0;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 f = __ldcg(reinterpret_cast<const float4*>(src + j));
-                                v[32 * hlf + j] += f.x; v[32 * hlf + j + 1] += f.y; v[32 * hlf + j + 2] += f.z; v[32 * hlf + j + 3] += f.w;
-                            }
-                        }
-                    } else {
+                    {
                         uint32_t r[32];
                         tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(lane_base) << 16) + c0, r);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[32 * hlf + j] = __uint_as_float(r[j]);
+                    }
+                    for (int z = 0; z < n_peers; ++z) {          // fixed order: deterministic sums
+                        const uint8_t* src = partial0 + (size_t)z * 128 * BN * 4;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 f = *reinterpret_cast<const float4*>(src + ((c0 + j) / 4 * 128 + row) * 16);
+                            v[32 * hlf + j] += f.x; v[32 * hlf + j + 1] += f.y; v[32 * hlf + j + 2] += f.z; v[32 * hlf + j + 3] += f.w;
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[32 * hlf + j] += sm.bias[c0 + j];
@@ -270,23 +298,20 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             float acc[32];
-            if (p.splits > 1) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-                for (int z = 0; z < p.splits; ++z) {
-                    const float* src = p.ws_partial + (((size_t)tile_lin * p.splits + z) * 128 + row) * BN + c0;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 f = __ldcg(reinterpret_cast<const float4*>(src + j));
-                        acc[j] += f.x; acc[j + 1] += f.y; acc[j + 2] += f.z; acc[j + 3] += f.w;
-                    }
-                }
-            } else {
+            {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem + (static_cast<uint32_t>(lane_base) << 16) + c0, r);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+            }
+            for (int z = 0; z < n_peers; ++z) {
+                const uint8_t* src = partial0 + (size_t)z * 128 * BN * 4;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 f = *reinterpret_cast<const float4*>(src + ((c0 + j) / 4 * 128 + row) * 16);
+                    acc[j] += f.x; acc[j + 1] += f.y; acc[j + 2] += f.z; acc[j + 3] += f.w;
+                }
             }
             const int n = n0 + c0;
             if (!pix_ok || n >= p.cout) continue;
@@ -357,10 +382,21 @@ int launch_conv(const ConvMaps& maps, const ConvP& p, int cout_pad, cudaStream_t
     static XmPerDevice attr_token = {0};
     const int smem = (int)sizeof(ConvSmem<BN, STAGES>) + 1024;
     if (xm_first_use_on_device(&attr_token)) {
-        XM_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        XM_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_csk_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     dim3 grid(p.tiles_x * p.tiles_y * p.batch, cout_pad / BN, p.splits);
-    XM_CHECK_CUDA(tc5_launch(conv_igemm_kernel<BN, STAGES>, grid, dim3(192), smem, stream, maps, p));
+    // the splits of one output tile are one cluster; the partial area must fit behind the TMA-store boxes of the A ring
+    static_assert(STAGES * 128 * 128 >= (BN / 64) * 128 * 128, "A ring smaller than the store boxes");
+    if ((int64_t)(p.splits - 1) * 128 * BN * 4 > (int64_t)(STAGES - BN / 64) * 128 * 128) return XM_ERR_ARG;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = p.splits;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = xm_pdl_enabled() ? 2 : 1;
+    XM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_csk_kernel<BN, STAGES>, maps, p));
     xm_count_launches(1);
     XM_CHECK_CUDA(cudaGetLastError());
     return XM_OK;
@@ -378,6 +414,22 @@ extern "C" int xm_conv2d_nhwc(const xm_conv_args_t* a, void* stream_) {
     XM_REQUIRE(a->cout >= 1 && a->cout_pad >= a->cout && a->cout_pad % 64 == 0, "xm_conv2d_nhwc: cout_pad must be a multiple of 64 >= cout");
     XM_REQUIRE(a->weight && a->bias && (a->out || a->out_relu), "xm_conv2d_nhwc: null weight/bias/out");
     XM_REQUIRE(a->out_stride >= a->out_offset + a->cout, "xm_conv2d_nhwc: out_stride too small");
+    {
+        // CTA pairs (conv_igemm_pair.cu) when the 128x128 tiling needs more than one wave but pairs with BN = 256 fit in one:
+        // each SM then ingests half the weight bytes per FLOP (the big layers are bound by per-SM TMA ingest)
+        const int Ho = a->H / (a->stride ? a->stride : 1), Wo = a->W / (a->stride ? a->stride : 1);
+        int best = -1;
+        for (int tw = 8; tw <= 32; tw *= 2) {
+            const int th = 128 / tw;
+            const int area = ((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
+            if (best < 0 || area < best) best = area;
+        }
+        const int mtiles = best * a->batch;
+        const int sms = xm_num_sms();
+        if (a->stride == 1 && a->cout_pad % 256 == 0 && a->cout % 64 == 0 && mtiles * (a->cout_pad / 128) > sms &&
+            ((mtiles + 1) / 2) * 2 * (a->cout_pad / 256) <= sms)
+            return xm_conv2d_pair(a, stream_);
+    }
     if (a->stride == 2) {
         XM_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, "xm_conv2d_nhwc: stride-2 needs even H, W");
         XM_REQUIRE(a->batch == 1, "xm_conv2d_nhwc: stride-2 convolutions are launched one image at a time");
@@ -473,24 +525,17 @@ extern "C" int xm_conv2d_nhwc(const xm_conv_args_t* a, void* stream_) {
     const int ksteps = a->ksize * a->ksize * cb_total;
     const int ctas = p.tiles_x * p.tiles_y * p.batch * (a->cout_pad / BN);
     const int sms = xm_num_sms();
+    // cluster split-K: put idle SMs on the layer (each CTA's K-step pulls 16 KB + BN*128 B through ITS SM's L2 port);
+    // every split keeps at least 8 k-steps, whole clusters must fit in one wave
     p.splits = 1;
-    if (a->workspace && ((ctas * 3 <= sms && ksteps >= 48) || (ctas * 2 <= sms && ksteps > 128))) {   // small grids, long K loops
-        int s = sms / ctas;
-        if (s > ksteps / 16) s = ksteps / 16;
-        if (s > 4) s = 4;
-        const int64_t need = 65536 * 4 + (int64_t)ctas * s * 128 * BN * 4;
-        if (s >= 2 && need <= a->workspace_bytes && ctas <= 65536) p.splits = s;
-    }
-    if (f_split > 0 && a->workspace && ctas <= 65536 && 65536 * 4 + (int64_t)ctas * f_split * 128 * BN * 4 <= a->workspace_bytes)
-        p.splits = f_split > ksteps ? ksteps : f_split;
+    const int max_split = (BN == 64) ? 3 : 2;            // room in the leader's A ring (6 stages), see the kernel header
+    while (p.splits < max_split && ctas * (p.splits + 1) <= sms && ksteps / (p.splits + 1) >= 8) ++p.splits;
+    if (f_split > 0) p.splits = f_split > max_split ? max_split : f_split;
+    if (p.splits > ksteps) p.splits = ksteps;
     p.ksteps_per_split = (ksteps + p.splits - 1) / p.splits;
-    p.splits = (ksteps + p.ksteps_per_split - 1) / p.ksteps_per_split;
-    p.ws_counter = (int*)a->workspace;
-    p.ws_partial = a->workspace ? (float*)((char*)a->workspace + 65536 * 4) : nullptr;
-    // pipeline depth: short K loops want several co-resident CTAs per SM (2 stages -> 3 CTAs/SM); long K loops on
-    // small grids want a deep ring to cover the L2 latency (6 stages, 1 CTA/SM); big grids take 3 stages (2 CTAs/SM).
-    int depth = (p.ksteps_per_split <= 4) ? 2 : ((ctas * p.splits < 2 * sms) ? 6 : 3);
-    if (f_depth == 2 || f_depth == 3 || f_depth == 6) depth = f_depth;
+    p.splits = (ksteps + p.ksteps_per_split - 1) / p.ksteps_per_split;      // no empty split: every CTA issues >= 1 MMA
+    int depth = (p.splits > 1) ? 6 : ((p.ksteps_per_split <= 4) ? 2 : ((ctas < 2 * sms) ? 6 : 3));
+    if (p.splits == 1 && (f_depth == 2 || f_depth == 3 || f_depth == 6)) depth = f_depth;
     if (BN == 128) {
         if (depth == 2) return launch_conv<128, 2>(maps, p, a->cout_pad, stream);
         if (depth == 3) return launch_conv<128, 3>(maps, p, a->cout_pad, stream);

@@ -1,4 +1,3 @@
-// EXPERIMENTAL (round-2 head start, NOT part of libxmem2_b200.so, never run on a GPU yet):
 // conv_igemm_2cta.cu — the production implicit-GEMM convolution (../conv_igemm.cu) on CTA PAIRS (tcgen05 cta_group::2):
 // two CTAs of a cluster (2,1,1) own two neighbouring 128-pixel tiles and the SAME BN output channels; the leader issues
 // one M=256 x N=BN MMA per 16 channels that reads A (128 pixel rows) from each CTA's own shared memory and B from BOTH
@@ -21,7 +20,6 @@
 // whose loads are zero-filled (batch coordinate out of range) and whose stores are clipped.
 // Compile check:  nvcc -gencode arch=compute_100a,code=sm_100a -c conv_igemm_2cta.cu
 //
-// (header of the production file follows)
 // conv_igemm.cu — implicit-GEMM convolution on tcgen05 for NHWC fp16 activations.
 //
 // One kernel serves every 1x1 / 3x3 (stride 1 or 2, padding k/2) convolution on the XMem++ path
@@ -43,8 +41,8 @@
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
 #include <cstdio>
 #include <cstdlib>
-#include "../common.h"
-#include "../tc5.cuh"
+#include "common.h"
+#include "tc5.cuh"
 
 using namespace tc5;
 
@@ -381,11 +379,10 @@ teardown:
 template <int BN, int STAGES>
 int launch_conv(const ConvMaps& maps, const ConvP& p, int cout_pad, cudaStream_t stream) {
     tc5_debug_init();
-    static bool attr_done = false;
+    static XmPerDevice attr_token = {0};
     const int smem = (int)sizeof(ConvSmem<BN, STAGES>) + 1024;
-    if (!attr_done) {
+    if (xm_first_use_on_device(&attr_token)) {
         XM_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_2cta_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
     }
     // epilogue staging: BN/64 output boxes in the A ring, BN/64 residual boxes in the B ring (16 KB each)
     static_assert(STAGES * 128 * 128 >= (BN / 64) * 128 * 128 && STAGES * (BN / 2) * 128 >= (BN / 64) * 128 * 128, "stage rings too small for the epilogue boxes");
@@ -406,7 +403,7 @@ int launch_conv(const ConvMaps& maps, const ConvP& p, int cout_pad, cudaStream_t
 
 }  // namespace
 
-extern "C" int xm_conv2d_nhwc_2cta(const xm_conv_args_t* a, void* stream_) {
+int xm_conv2d_pair(const xm_conv_args_t* a, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     XM_REQUIRE(a, "xm_conv2d_nhwc: null args");
     XM_REQUIRE(a->n_src >= 1 && a->n_src <= 3, "xm_conv2d_nhwc: n_src must be 1..3");

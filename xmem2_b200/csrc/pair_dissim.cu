@@ -1,4 +1,3 @@
-// EXPERIMENTAL (round-2 head start, NOT part of libxmem2_b200.so, never run on a GPU yet):
 // pair_dissim.cu — fused cycle dissimilarity of ordered frame pairs for the annotation-candidate selector
 // (reference inference/frame_selection/frame_selection.py:213-221):
 //     score(A, B) = mean over [HW, HW] of relu(S_ab[x, y] - S_ba[x, y])
@@ -16,8 +15,8 @@
 // writes 4 bytes.  Compile check:  nvcc -gencode arch=compute_100a,code=sm_100a -c pair_dissim.cu
 #include <cstdio>
 #include <cstdlib>
-#include "../common.h"
-#include "../tc5.cuh"
+#include "common.h"
+#include "tc5.cuh"
 
 using namespace tc5;
 
@@ -167,11 +166,10 @@ extern "C" int xm_pair_dissimilarity(const void* kp_all, const void* qp_all, con
         if (xm_make_tmap_f16(&maps.kp, kp_all, 3, d, st, b)) return XM_ERR_CUDA;
         if (xm_make_tmap_f16(&maps.qp, qp_all, 3, d, st, b)) return XM_ERR_CUDA;
     }
-    static bool attr_done = false;
+    static XmPerDevice attr_token = {0};
     const int smem = (int)sizeof(PairSmem) + 1024;
-    if (!attr_done) {
+    if (xm_first_use_on_device(&attr_token)) {
         XM_CHECK_CUDA(cudaFuncSetAttribute(pair_dissim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
     }
     const int tiles = hw_pad / PT;
     XM_CHECK_CUDA(tc5_launch(pair_dissim_kernel, dim3(tiles, tiles, n_pairs), dim3(192), smem, stream, maps, bsq_all, ms_all, (int)hw_pad,

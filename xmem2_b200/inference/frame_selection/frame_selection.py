@@ -17,7 +17,6 @@ A fused pair kernel (both score tiles in TMEM, relu-difference reduced in the ep
 from __future__ import annotations
 
 import ctypes as C
-import os
 from typing import List
 
 import numpy as np
@@ -67,6 +66,7 @@ class _PackedFrames:
         self.hw_pad = (self.hw + 127) // 128 * 128
         self.cap = (self.hw + 7) // 8 * 8 + 64
         self.frames = {}
+        self.device = dev
         for i, ok in enumerate(valid):
             if not ok:
                 continue
@@ -78,37 +78,14 @@ class _PackedFrames:
             ms[:self.hw] = shrinkages[i].reshape(-1).float()
             qp, bsq = lib.query_pack(krows, erows, self.hw_pad)
             self.frames[i] = (kp, ms, qp, bsq)
-        # the read kernel wants a value bank and a readout buffer; neither is looked at here
-        self.values = torch.zeros((1, CV, self.cap), dtype=torch.float16, device=dev)
-        self.readout = torch.empty((1, self.hw, CV), dtype=torch.float16, device=dev)
-        wsb = lib.load().xm_affinity_workspace_bytes(self.hw, 1)
-        self.ws = lib.affinity_workspace(self.hw, 1, dev)
-        self.scores = [torch.empty((self.hw, self.hw_pad), dtype=torch.float32, device=dev) for _ in range(2)]
-
-    def similarity(self, mem: int, query: int, out: torch.Tensor, top_k: int):
-        """out[n, q] = S(memory pixel n of frame `mem`, query pixel q of frame `query`)  (memory_util.py:7-39)."""
-        kp, ms, _, _ = self.frames[mem]
-        _, _, qp, bsq = self.frames[query]
-        a = lib.XmAffinityArgs()
-        a.banks[0].size = 0; a.banks[2].size = 0
-        b = a.banks[1]
-        b.keys, b.shrinkage, b.values, b.usage = kp.data_ptr(), ms.data_ptr(), self.values.data_ptr(), None
-        b.cap, b.n_obj_cap, b.size = self.cap, 1, self.hw
-        a.n_groups = 1
-        a.groups[0].obj_begin, a.groups[0].n_obj = 0, 1
-        a.qp, a.bsq, a.hw, a.hw_pad, a.top_k, a.n_obj_total = qp.data_ptr(), bsq.data_ptr(), self.hw, self.hw_pad, top_k, 1
-        a.readout_chw, a.readout_hwc = None, self.readout.data_ptr()
-        a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
-        a.debug_scores = out.data_ptr()
-        a.plan_is_resident = 0
-        lib.check(lib.load().xm_affinity_readout(C.byref(a), lib.stream_ptr()), 'xm_affinity_readout')
 
 
-def _pair_scores_fused(packed: _PackedFrames, chosen: int, candidates: List[int]) -> torch.Tensor:
-    """Development path (XMEM_PAIR_IMPL=fused): csrc/experimental/pair_dissim.cu, one launch for all candidates; both score
-    tiles stay in TMEM.  Not validated yet — see csrc/experimental/README.md."""
-    L = lib.load_experimental()
-    dev = packed.values.device
+def _pair_scores(packed: _PackedFrames, chosen: int, candidates: List[int]) -> torch.Tensor:
+    """cycle dissimilarity of (A = `chosen`, B = j) for every j in `candidates` (reference :213-221) -> fp32 [len]:
+    csrc/pair_dissim.cu, one launch for all candidates; both 128x128 score tiles of a pair stay in TMEM and only the
+    relu-difference sums leave the kernel."""
+    L = lib.load()
+    dev = packed.device
     if not hasattr(packed, 'stacked'):
         ids = sorted(packed.frames)
         slot = {f: i for i, f in enumerate(ids)}
@@ -135,21 +112,6 @@ def _pair_scores_fused(packed: _PackedFrames, chosen: int, candidates: List[int]
                                      lib.stream_ptr())
         if rc != 0:
             raise RuntimeError(f'xm_pair_dissimilarity failed ({rc}): {L.xm_last_error().decode()}')
-    return out
-
-
-def _pair_scores(packed: _PackedFrames, chosen: int, candidates: List[int]) -> torch.Tensor:
-    """cycle dissimilarity of (A = `chosen`, B = j) for every j in `candidates` (reference :213-221) -> fp32 [len]."""
-    if os.environ.get('XMEM_PAIR_IMPL', '') == 'fused':
-        return _pair_scores_fused(packed, chosen, candidates)
-    hw = packed.hw
-    top_k = min(30, hw)
-    s_ab, s_ba = packed.scores
-    out = torch.empty(len(candidates), dtype=torch.float32, device=s_ab.device)
-    for n, j in enumerate(candidates):
-        packed.similarity(chosen, j, s_ab, top_k)
-        packed.similarity(j, chosen, s_ba, top_k)
-        out[n] = F.relu(s_ab[:, :hw] - s_ba[:, :hw]).sum() / (hw * hw)
     return out
 
 

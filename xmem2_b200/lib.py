@@ -96,6 +96,7 @@ def load() -> C.CDLL:
         lib.xm_upsample4x_aggregate.argtypes = [vp, i32, i32, i32, vp, vp, vp]
         lib.xm_resize_argmax.argtypes = [vp, i32, i32, i32, i64, i64, i32, i32, vp, vp, vp]
         lib.xm_value_append.argtypes = [vp, i32, i32, vp, i64, i32, vp]
+        lib.xm_pair_dissimilarity.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, i32, vp, vp, vp]
         _lib = lib
     return _lib
 
@@ -187,45 +188,5 @@ def conv2d_nhwc(srcs, weight, bias, cout, ksize=3, stride=1, relu=False, residua
     a.out_stride, a.out_offset = ref.shape[3], out_offset
     ws = conv_workspace(t0.device)
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-    if _CONV_IMPL and _experimental_conv(a):
-        return out, out_relu
     check(load().xm_conv2d_nhwc(C.byref(a), stream_ptr()), 'xm_conv2d_nhwc')
     return out, out_relu
-
-
-# ---------------------------------------------------------------------------------------------------------------------
-# Development switch (round-2 head starts, csrc/experimental/): XMEM_CONV_IMPL=csk|2cta|mc|halo routes the convolutions the
-# variant supports to libxmem2_b200_exp.so (`python -m xmem2_b200.build --experimental`).  Unset (the default, and the
-# only configuration that has been validated and measured) the product library serves every convolution.
-_CONV_IMPL = os.environ.get('XMEM_CONV_IMPL', '')
-_exp_lib = None
-
-
-def load_experimental() -> C.CDLL:
-    global _exp_lib
-    if _exp_lib is None:
-        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libxmem2_b200_exp.so')
-        if not os.path.exists(path):
-            raise RuntimeError(f'{path} not found: build it with `python -m xmem2_b200.build --experimental`')
-        _exp_lib = C.CDLL(path)
-        _exp_lib.xm_last_error.restype = C.c_char_p
-        for name in ('xm_conv2d_nhwc_csk', 'xm_conv2d_nhwc_2cta', 'xm_conv2d_nhwc_mc', 'xm_conv2d_nhwc_halo'):
-            getattr(_exp_lib, name).argtypes = [C.POINTER(XmConvArgs), C.c_void_p]
-        vp, i32 = C.c_void_p, C.c_int32
-        _exp_lib.xm_pair_dissimilarity.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, i32, vp, vp, vp]
-    return _exp_lib
-
-
-def _experimental_conv(a) -> bool:
-    """True if the selected experimental variant took the call (it raises on a CUDA/launch error)."""
-    if _CONV_IMPL not in ('csk', '2cta', 'mc', 'halo'):
-        raise RuntimeError(f'XMEM_CONV_IMPL={_CONV_IMPL!r}: expected csk, 2cta, mc or halo')
-    if _CONV_IMPL in ('2cta', 'mc') and a.cout_pad % 128 != 0:
-        return False                                  # pair/multicast variants need whole 128-channel tiles
-    if _CONV_IMPL == 'halo' and (a.ksize != 3 or a.stride != 1):
-        return False                                  # the haloed-tile variant serves 3x3 stride-1 convolutions only
-    L = load_experimental()
-    rc = getattr(L, 'xm_conv2d_nhwc_' + _CONV_IMPL)(C.byref(a), stream_ptr())
-    if rc != 0:
-        raise RuntimeError(f'xm_conv2d_nhwc_{_CONV_IMPL} failed ({rc}): {L.xm_last_error().decode()}')
-    return True
