@@ -9,22 +9,7 @@ from xmem2_b200 import lib
 CK, CV = 64, 512
 
 
-def make_case(hw, sizes, n_obj, group_begins, seed=0, device='cuda', key_scale=0.6):
-    """sizes = (long, work, perm) columns; group_begins = list of (obj_begin, n_obj, [b_long, b_work, b_perm])."""
-    g = torch.Generator().manual_seed(seed)
-    banks = []
-    for n in sizes:
-        cap = max(8, (n + 64 + 7) // 8 * 8)
-        if n == 0:
-            banks.append(None); continue
-        key = (torch.randn(n, CK, generator=g) * key_scale).half()
-        shr = (torch.rand(n, generator=g) * 2 + 1).float()
-        val = torch.zeros(n_obj, CV, cap).half()
-        val[:, :, :n] = torch.randn(n_obj, CV, n, generator=g).half()
-        banks.append(dict(key=key, shr=shr, val=val, cap=cap, n=n))
-    qk = (torch.randn(hw, CK, generator=g) * key_scale).half()
-    qe = torch.rand(hw, CK, generator=g).half()
-    return dict(hw=hw, banks=banks, n_obj=n_obj, groups=group_begins, qk=qk, qe=qe, device=device)
+from xmem2_b200.util.synth_memory import make_case      # noqa: E402,F401  (shared with bench.py)
 
 
 def case_from_attention_golden(device='cuda'):

@@ -19,6 +19,6 @@ fac = lambda: InferenceCore(net, dict(cfg))
 bench.run_clip(fac, frames[:12], {0: masks[0]}, dev, False)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-bench.run_clip(fac, frames[:n], {k: v for k, v in masks.items()}, dev, False)
+bench.run_clip(fac, frames[:n], {k: v for k, v in masks.items() if k < n}, dev, False)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()

@@ -70,7 +70,15 @@ def run(rank, world, hw, frame, n_frames, n_obj, iters, out_path=None):
         exp_out, _, amb, _ = k1_ref.expected(case)
         err = (out.float().cpu().permute(0, 2, 1).double() - exp_out).abs().amax(dim=(0, 1))
         res['oracle_err_clear'] = err[~amb].max().item()
+        err1 = (ref.float().cpu().permute(0, 2, 1).double() - exp_out).abs().amax(dim=(0, 1))
+        res['oracle_err_clear_1gpu'] = err1[~amb].max().item()
+        res['ambiguous'] = int(amb.sum())
+        bad = (err1 > 2e-2) & ~amb
+        res['bad_queries_1gpu'] = [int(i) for i in torch.nonzero(bad).flatten()[:12]]
+        res['n_bad_1gpu'] = int(bad.sum())
     if iters:
+        for _ in range(5):                     # NCCL sets its channels up lazily: keep that out of the timed loop
+            reader.read(a, out)
         dist.barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -80,6 +88,36 @@ def run(rank, world, hw, frame, n_frames, n_obj, iters, out_path=None):
         t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         res['ms_per_read'] = t.item()
+        if os.environ.get('TSHARD_HOSTPROF'):
+            import time, cProfile, pstats, io
+            pr = cProfile.Profile(); pr.enable()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                reader.read(a, out)
+            t1 = time.perf_counter()
+            torch.cuda.synchronize()
+            pr.disable()
+            if rank == 0:
+                sio = io.StringIO(); pstats.Stats(pr, stream=sio).sort_stats('cumulative').print_stats(14)
+                print(f'host time per read (no sync): {(t1 - t0) / 5 * 1e3:.2f} ms'); print(sio.getvalue()[:2500], flush=True)
+        st = []
+        reader.read(a, out, stage_times=st)
+        res['stage_ms'] = dict(zip(['stage_a', 'allreduce_max', 'stage_b', 'allgather', 'merge+stage_c', 'allreduce_sum', 'cast'],
+                                   [round(x, 4) for x in st]))
+        if rank == 0:
+            # single-GPU read of the WHOLE memory, timed the same way
+            a1, keep1 = build_args(case, list(range(frame * n_frames)), dev)
+            ref = torch.zeros(n_obj, hw, CV, dtype=torch.float16, device=dev)
+            a1.readout_hwc = ref.data_ptr(); a1.plan_is_resident = 0
+            for _ in range(3):
+                lib.check(lib.load().xm_affinity_readout(C.byref(a1), lib.stream_ptr()), 'xm_affinity_readout')
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                lib.check(lib.load().xm_affinity_readout(C.byref(a1), lib.stream_ptr()), 'xm_affinity_readout')
+            e1.record(); torch.cuda.synchronize()
+            res['ms_per_read_1gpu'] = e0.elapsed_time(e1) / iters
     if rank == 0:
         res.update(world=world, hw=hw, N=frame * n_frames, n_obj=n_obj)
         print(json.dumps(res), flush=True)

@@ -63,27 +63,45 @@ class ShardedReader:
                 acc=torch.empty((n_obj, hw_pad, lib.CV), dtype=torch.float32, device=device))
         return self._bufs[key]
 
-    def read(self, args: "lib.XmAffinityArgs", out_hwc: torch.Tensor):
-        """`args`: banks/groups[0]/query/workspace of THIS rank (see MemoryManager._read_args); out_hwc [n_obj][hw][512] fp16."""
+    def read(self, args: "lib.XmAffinityArgs", out_hwc: torch.Tensor, stage_times: list = None):
+        """`args`: banks/groups[0]/query/workspace of THIS rank (see MemoryManager._read_args); out_hwc [n_obj][hw][512] fp16.
+        `stage_times` (diagnostics): receives the CUDA-event milliseconds of the 8 steps."""
         L = _bind()
         dev = out_hwc.device
         b = self._buffers(args.hw_pad, args.n_obj_total, dev)
         st = lib.stream_ptr()
+        ev = []
+
+        def mark():
+            if stage_times is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(); ev.append(e)
+
+        mark()
         lib.check(L.xm_affinity_tshard_stage_a(C.byref(args), b['tau_lo'].data_ptr(), st), 'tshard_stage_a')
+        mark()
         if self.world > 1:
             dist.all_reduce(b['tau_lo'], op=dist.ReduceOp.MAX, group=self.group)
+        mark()
         lib.check(L.xm_affinity_tshard_stage_b(C.byref(args), b['tau_lo'].data_ptr(), b['top32'].data_ptr(), st), 'tshard_stage_b')
+        mark()
         if self.world > 1:
             dist.all_gather_into_tensor(b['gathered'], b['top32'], group=self.group)
             gathered = b['gathered']
         else:
             gathered = b['top32']
+        mark()
         lib.check(L.xm_affinity_tshard_merge(gathered.data_ptr(), self.world, args.hw, args.hw_pad, args.top_k, b['tau'].data_ptr(),
                                              b['inv_den'].data_ptr(), st), 'tshard_merge')
         lib.check(L.xm_affinity_tshard_stage_c(C.byref(args), b['tau'].data_ptr(), b['inv_den'].data_ptr(), b['acc'].data_ptr(), st),
                   'tshard_stage_c')
+        mark()
         if self.world > 1:
             dist.all_reduce(b['acc'], op=dist.ReduceOp.SUM, group=self.group)
+        mark()
         lib.check(L.xm_affinity_tshard_cast(b['acc'].data_ptr(), args.n_obj_total, args.hw, args.hw_pad, None, out_hwc.data_ptr(), st),
                   'tshard_cast')
+        mark()
+        if stage_times is not None:
+            torch.cuda.synchronize()
+            stage_times[:] = [ev[i].elapsed_time(ev[i + 1]) for i in range(len(ev) - 1)]
         return out_hwc, b['tau']
