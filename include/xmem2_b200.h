@@ -178,6 +178,29 @@ int xm_upsample4x_aggregate(const void* logits4, int32_t n, int32_t h4, int32_t 
 /* value fp16 [n_obj][hw][512] (NHWC) -> arena fp16 [n_obj][512][cap] columns [col0, col0+hw)               */
 int xm_value_append(const void* value_hwc, int32_t n_obj, int32_t hw, void* arena, int64_t cap, int32_t col0, void* stream);
 
+/* ---------------------------------------------------------------- long-term memory maintenance */
+/* torch.topk(use/life, k, sorted=True) of inference/memory_manager.py:355: indices by descending usage, ties by ascending index. */
+int xm_usage_topk(const float* use, const float* life, int32_t n, int32_t k, int32_t* out_idx, void* stream);
+/* least-used eviction of inference/kv_memory_store.py:160-181: thr = n_remove-th smallest use/life; keep_idx <- ascending columns
+ * with use/life > thr, *count <- their number (device int32; the host reads it to update its bookkeeping). */
+int xm_usage_evict_list(const float* use, const float* life, int32_t n, int32_t n_remove, int32_t* keep_idx, int32_t* count, void* stream);
+/* consolidation (inference/memory_manager.py:349-390): for every prototype q with proto_idx[q] >= col_begin,
+ *   aff[q][n] = softmax over n in [col_begin, n) of similarity(candidate n, prototype q)   (model/memory_util.py:7-39,55-60)
+ *   shr_out[q] = sum_n s[n] * aff[q][n]                                                    (optional)
+ * kp fp16 [n][128] packed candidate keys (xm_key_pack), s fp32 [n], e fp16 [n][64] selection rows or NULL. */
+int xm_consolidate_affinity(const void* kp, const float* s, const void* e, int32_t n, const int32_t* proto_idx, int32_t n_proto,
+                            int32_t col_begin, float* aff, int64_t aff_stride, float* shr_out, void* stream);
+int64_t xm_consolidate_scratch_bytes(int32_t n_obj, int32_t n_valid);
+/* out fp16 [n_obj][512][n_valid] = v[o][c][col_begin..n) @ aff[valid_q[j]][col_begin..n)^T; v fp16 planes with column pitch `cap`;
+ * valid_q NULL = prototypes 0..n_valid-1. */
+int xm_consolidate_values(const void* v, int64_t cap, int32_t n_obj, int32_t col_begin, int32_t n, const float* aff, int64_t aff_stride,
+                          const int32_t* valid_q, int32_t n_valid, float* scratch, int64_t scratch_bytes, void* out, void* stream);
+/* in-arena compaction of a bank (inference/kv_memory_store.py:125-158,178-181): column i in [first, m) <- column keep_idx[i]
+ * (or i + shift when keep_idx is NULL), source >= destination, through the scratch `tmp`. */
+int64_t xm_bank_compact_tmp_bytes(int32_t n_obj_cap, int32_t moved);
+int xm_bank_compact(void* kp, float* s, void* e, float* use, float* life, void* v, int64_t cap, int32_t n_obj_cap, const int32_t* keep_idx,
+                    int32_t shift, int32_t first, int32_t m, void* tmp, int64_t tmp_bytes, void* stream);
+
 /* ---------------------------------------------------------------- annotation-candidate selector */
 /* Cycle dissimilarity of ordered frame pairs (inference/frame_selection/frame_selection.py:213-221):
  *   out[p] = mean over [hw, hw] of relu(S_ab - S_ba),  A = pair_a[p], B = pair_b[p], S as in model/memory_util.py:7-39.

@@ -21,12 +21,8 @@ HW = H * W
 
 @pytest.fixture
 def ref_manager_cls(monkeypatch):
-    def key_pack(key_rows, dst_rows):
-        k = key_rows.float()
-        dst_rows[:, :CK] = (k * k).half()
-        dst_rows[:, CK:] = key_rows
-    monkeypatch.setattr(lib, 'require_cuda', lambda t, name: None)
-    monkeypatch.setattr(lib, 'key_pack', key_pack)
+    from tests import cpu_doubles
+    cpu_doubles.install(monkeypatch, lib)
     monkeypatch.setattr(kv, '_ARENA_POOL', {})
     saved = {k: v for k, v in sys.modules.items() if k.split('.')[0] in ('inference', 'model', 'util')}
     for k in saved:

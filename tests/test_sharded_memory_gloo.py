@@ -20,12 +20,10 @@ def _install_cpu_doubles():
     from xmem2_b200 import lib
     from xmem2_b200.inference import kv_memory_store as kv
 
-    def key_pack(key_rows, dst_rows):
-        k = key_rows.float()
-        dst_rows[:, :CK] = (k * k).half()
-        dst_rows[:, CK:] = key_rows
+    from tests import cpu_doubles
     lib.require_cuda = lambda t, name: None
-    lib.key_pack = key_pack
+    for name in ('key_pack', 'usage_topk', 'usage_evict_list', 'consolidate_affinity', 'consolidate_values', 'bank_compact'):
+        setattr(lib, name, getattr(cpu_doubles, name))
     kv._ARENA_POOL.clear()
 
 

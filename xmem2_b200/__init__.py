@@ -1,7 +1,7 @@
 """xmem2_b200 — B200-native implementation of the XMem++ per-frame memory-attention inference path.
 
 Module paths mirror the reference repository (`inference.inference_core`, `inference.memory_manager`,
-`inference.kv_memory_store`, `inference.frame_selection.frame_selection`, `model.network`, `model.memory_util`,
+`inference.kv_memory_store`, `inference.frame_selection.frame_selection`, `model.network`,
 `model.aggregate`; `util.tensor_util` and
 `util.configuration` exist for internal use).  `install()` registers them under those top-level names so the reference's own drivers
 (`process_video.py`, `inference/run_on_video.py`) import this implementation unchanged — see INTEGRATION.md.
@@ -15,7 +15,7 @@ __version__ = '0.1.0'
 # (compute_array_iou, the argparse Configuration) and their pad/unpad/VIDEO_INFERENCE_CONFIG are semantically identical
 # to the copies this package uses internally.
 _DROP_IN = ['inference.inference_core', 'inference.memory_manager', 'inference.kv_memory_store', 'model.network',
-            'model.memory_util', 'model.aggregate', 'inference.frame_selection.frame_selection']
+            'model.aggregate', 'inference.frame_selection.frame_selection']
 
 
 def install():

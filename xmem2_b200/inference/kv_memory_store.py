@@ -250,32 +250,36 @@ class KeyValueMemoryStore:
             return
         tail = n - b
         if tail > 0:
-            for t in (self._kp, self._s, self._e, self._use, self._life):
-                t[a:a + tail] = t[b:n].clone()
-            self._v[:, :, a:a + tail] = self._v[:, :, b:n].clone()
+            self._compact(None, cut, a, a + tail)
         for gi, g0 in enumerate(self._group_begin):
             if n - g0 < min_size and g0 < b:
                 raise NotImplementedError('a value group below min_size overlaps the sieved range')
             self._group_begin[gi] = g0 if g0 <= a else (a if g0 < b else g0 - cut)
         self._n = n - cut
 
+    def _compact(self, keep_idx, shift: int, first: int, m: int):
+        """columns [first, m) of every arena <- columns keep_idx[i] (or i + shift): csrc/consolidate.cu, xm_bank_compact."""
+        if m > first:
+            lib.bank_compact(self._kp, self._s, self._e, self._use, self._life, self._v, keep_idx, shift, first, m)
+
     def remove_obsolete_features(self, max_size: int):
-        """evict the least-used columns (kv_memory_store.py:160-181); strict '>' so threshold ties go too."""
-        usage = self.get_usage().flatten()
-        values, _ = torch.topk(usage, k=(self.size - max_size), largest=False, sorted=True)
-        survived = usage > values[-1]
+        """evict the least-used columns (kv_memory_store.py:160-181); strict '>' so threshold ties go too.  The threshold
+        (k-th smallest usage), the survivor list and the compaction run on the device; the host only reads the new size."""
+        if not self.count_usage:
+            raise RuntimeError('I did not count usage!')
         if self.num_groups > 1:
             raise NotImplementedError('The current data structure does not support feature removal with multiple object groups')
-        self.keep_columns(survived)
+        n = self._n
+        keep, m = lib.usage_evict_list(self._use, self._life, n, n - max_size)
+        self._compact(keep, 0, 0, m)
+        self._n = m
+        self._group_begin = [0 for _ in self._group_begin]
 
     def keep_columns(self, survived):
         """in-place compaction to the columns where the boolean mask `survived` [size] is set (single value group)."""
-        idx = torch.nonzero(survived).flatten()
+        idx = torch.nonzero(survived).flatten().to(torch.int32)
         m = idx.numel()
-        self._kp[:m] = self._kp[idx]; self._s[:m] = self._s[idx]; self._e[:m] = self._e[idx]
-        self._use[:m] = self._use[idx]; self._life[:m] = self._life[idx]
-        for grp in self.obj_groups:
-            self._v[grp[0]:grp[-1] + 1, :, :m] = self._v[grp[0]:grp[-1] + 1][:, :, idx]
+        self._compact(idx, 0, 0, m)
         self._n = m
         self._group_begin = [0 for _ in self._group_begin]
 

@@ -246,8 +246,8 @@ class MemoryManager:
 
     # ------------------------------------------------------------------ consolidation (reference :316-390)
     def compress_features(self):
-        """Move the oldest working-memory columns into `num_prototypes` long-term prototypes.  Low-frequency
-        (every (max-min) memory frames); runs as a few library ops on arena views."""
+        """Move the oldest working-memory columns into `num_prototypes` long-term prototypes (reference :316-347): prototype
+        selection, similarity, softmax and read-outs in csrc/consolidate.cu, the sieve as an in-arena compaction kernel."""
         HW = self.HW
         temp = self.temporary_work_mem
         total = temp.size
@@ -267,21 +267,48 @@ class MemoryManager:
                           group_objects=temp.obj_groups)
 
     def consolidation(self, candidate_key, candidate_shrinkage, candidate_selection, usage, candidate_value):
-        from ..model.memory_util import get_similarity, do_softmax
+        """Reference signature (:349-390).  candidate_key [1,CK,N], candidate_shrinkage [1,1,N], candidate_selection [1,CK,N] or
+        None, usage [1,1,N], candidate_value: per group [n_g,CV,N_g] (the group's LAST N_g candidates) or None.
+        Prototype selection, similarity + full softmax, value and shrinkage read-out run as CUDA kernels (csrc/consolidate.cu);
+        returns (prototype_key [1,CK,P], [prototype_value_g [n_g,CV,P_g] or None], prototype_shrinkage [1,1,P])."""
+        dev = candidate_key.device
+        lib.require_cuda(candidate_key, 'candidate_key')
         N = candidate_key.shape[-1]
-        _, max_usage_indices = torch.topk(usage, k=self.num_prototypes, dim=-1, sorted=True)
-        prototype_indices = max_usage_indices.flatten()
-        validity = [prototype_indices >= (N - gv.shape[2]) if gv is not None else None for gv in candidate_value]
-        prototype_key = candidate_key[:, :, prototype_indices]
-        prototype_selection = candidate_selection[:, :, prototype_indices] if candidate_selection is not None else None
-        similarity = get_similarity(candidate_key.float(), candidate_shrinkage, prototype_key.float(),
-                                    prototype_selection.float() if prototype_selection is not None else None)
-        affinity = [do_softmax(similarity[:, N - gv.shape[2]:, validity[gi]]) if gv is not None else None
-                    for gi, gv in enumerate(candidate_value)]
-        affinity = [aff if aff is None or aff.shape[-1] > 0 else None for aff in affinity]
-        prototype_value = [(gv.float() @ affinity[gi]) if affinity[gi] is not None else None
-                           for gi, gv in enumerate(candidate_value)]
-        prototype_shrinkage = (candidate_shrinkage @ affinity[0]) if candidate_shrinkage is not None else None
+        P = self.num_prototypes
+        u = usage.reshape(-1).float().contiguous()
+        proto = lib.usage_topk(u, torch.ones_like(u), P)
+        # candidates in the kernel's layout: packed key rows, fp32 shrinkage, fp16 selection rows
+        krows = candidate_key[0].transpose(0, 1).to(torch.float16).contiguous()
+        kp = torch.empty((N, 2 * lib.CK), dtype=torch.float16, device=dev)
+        lib.key_pack(krows, kp)
+        s = candidate_shrinkage.reshape(-1).float().contiguous()
+        e = candidate_selection[0].transpose(0, 1).to(torch.float16).contiguous() if candidate_selection is not None else None
+        n_pad = (N + 7) // 8 * 8
+        aff = torch.empty((P, n_pad), dtype=torch.float32, device=dev)
+        shr_out = torch.empty(P, dtype=torch.float32, device=dev)
+        prototype_value = []
+        first = True
+        for gv in candidate_value:
+            if gv is None:
+                prototype_value.append(None)
+                continue
+            ng = gv.shape[2]
+            col_begin = N - ng
+            lib.consolidate_affinity(kp, s, e, proto, col_begin, aff, shr_out if first else None)
+            first = False
+            if col_begin == 0:
+                valid, n_valid = None, P
+            else:       # prototypes outside this group's columns do not exist for it (:357-359); the host needs the count
+                valid = torch.nonzero(proto >= col_begin).flatten().to(torch.int32)
+                n_valid = int(valid.numel())
+            if n_valid == 0:
+                prototype_value.append(None)
+                continue
+            if not (gv.stride(2) == 1 and gv.stride(0) == gv.shape[1] * gv.stride(1) and gv.dtype == torch.float16):
+                gv = gv.to(torch.float16).contiguous()
+            prototype_value.append(lib.consolidate_values(gv, aff, col_begin, valid, n_valid))
+        prototype_key = candidate_key[:, :, proto.long()]
+        prototype_shrinkage = shr_out.view(1, 1, P) if candidate_shrinkage is not None else None
         return prototype_key, prototype_value, prototype_shrinkage
 
     # ------------------------------------------------------------------ GUI helper (reference :392-425)

@@ -97,6 +97,15 @@ def load() -> C.CDLL:
         lib.xm_resize_argmax.argtypes = [vp, i32, i32, i32, i64, i64, i32, i32, vp, vp, vp]
         lib.xm_value_append.argtypes = [vp, i32, i32, vp, i64, i32, vp]
         lib.xm_pair_dissimilarity.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, i32, vp, vp, vp]
+        lib.xm_usage_topk.argtypes = [vp, vp, i32, i32, vp, vp]
+        lib.xm_usage_evict_list.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+        lib.xm_consolidate_affinity.argtypes = [vp, vp, vp, i32, vp, i32, i32, vp, i64, vp, vp]
+        lib.xm_consolidate_scratch_bytes.restype = C.c_int64
+        lib.xm_consolidate_scratch_bytes.argtypes = [i32, i32]
+        lib.xm_consolidate_values.argtypes = [vp, i64, i32, i32, i32, vp, i64, vp, i32, vp, i64, vp, vp]
+        lib.xm_bank_compact_tmp_bytes.restype = C.c_int64
+        lib.xm_bank_compact_tmp_bytes.argtypes = [i32, i32]
+        lib.xm_bank_compact.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp, i32, i32, i32, vp, i64, vp]
         _lib = lib
     return _lib
 
@@ -190,3 +199,53 @@ def conv2d_nhwc(srcs, weight, bias, cout, ksize=3, stride=1, relu=False, residua
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     check(load().xm_conv2d_nhwc(C.byref(a), stream_ptr()), 'xm_conv2d_nhwc')
     return out, out_relu
+
+
+# ------------------------------------------------------------------------------------------------
+# long-term memory maintenance (csrc/consolidate.cu); tensor-level wrappers so that the CPU host-logic tests can replace them
+# ------------------------------------------------------------------------------------------------
+def usage_topk(use: torch.Tensor, life: torch.Tensor, k: int) -> torch.Tensor:
+    """indices (int32 [k]) of the k largest use/life, descending, ties by ascending index (memory_manager.py:355)."""
+    require_cuda(use, 'usage')
+    n = use.numel()
+    out = torch.empty(k, dtype=torch.int32, device=use.device)
+    check(load().xm_usage_topk(ptr(use), ptr(life), n, k, ptr(out), stream_ptr()), 'xm_usage_topk')
+    return out
+
+
+def usage_evict_list(use: torch.Tensor, life: torch.Tensor, n: int, n_remove: int):
+    """(keep_idx int32 [n] of which the first `count` are valid, count): columns with use/life above the n_remove-th smallest."""
+    keep = torch.empty(n, dtype=torch.int32, device=use.device)
+    count = torch.zeros(1, dtype=torch.int32, device=use.device)
+    check(load().xm_usage_evict_list(ptr(use), ptr(life), n, n_remove, ptr(keep), ptr(count), stream_ptr()), 'xm_usage_evict_list')
+    return keep, int(count.item())
+
+
+def consolidate_affinity(kp, s, e, proto, col_begin: int, aff, shr_out):
+    """aff[q, col_begin:n] <- softmax_n similarity(candidate n, prototype q) for prototypes with proto[q] >= col_begin; shr_out optional."""
+    n = kp.shape[0]
+    check(load().xm_consolidate_affinity(ptr(kp), ptr(s), ptr(e), n, ptr(proto), proto.numel(), col_begin, ptr(aff), aff.stride(0),
+                                         ptr(shr_out), stream_ptr()), 'xm_consolidate_affinity')
+
+
+def consolidate_values(gv, aff, col_begin: int, valid, n_valid: int) -> torch.Tensor:
+    """gv [n_g, CV, N_g] fp16 (last dim contiguous, channel pitch gv.stride(1)) @ aff[valid][:, col_begin:col_begin+N_g]^T -> [n_g, CV, n_valid]."""
+    L = load()
+    n_g, _, ng = gv.shape
+    sb = L.xm_consolidate_scratch_bytes(n_g, n_valid)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=gv.device)
+    out = torch.empty((n_g, CV, n_valid), dtype=torch.float16, device=gv.device)
+    check(L.xm_consolidate_values(ptr(gv), gv.stride(1), n_g, 0, ng, aff.data_ptr() + 4 * col_begin, aff.stride(0), ptr(valid), n_valid,
+                                  ptr(scratch), sb, ptr(out), stream_ptr()), 'xm_consolidate_values')
+    return out
+
+
+def bank_compact(kp, s, e, use, life, v, keep_idx, shift: int, first: int, m: int):
+    """columns [first, m) of every arena of a bank <- columns keep_idx[i] (or i + shift), in place."""
+    L = load()
+    n_planes, cap = v.shape[0], v.shape[2]
+    tb = L.xm_bank_compact_tmp_bytes(n_planes, m - first)
+    tmp = torch.empty(tb, dtype=torch.uint8, device=kp.device)
+    check(L.xm_bank_compact(ptr(kp), ptr(s), ptr(e), ptr(use), ptr(life), ptr(v), cap, n_planes, ptr(keep_idx), shift, first, m, ptr(tmp), tb,
+                            stream_ptr()), 'xm_bank_compact')
+
