@@ -134,11 +134,11 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': self.max_mhz, 'reasons': reasons, 'samples': len(sm)}
 
 
-def k1_roofline(device):
-    """CUDA-event timing of xm_affinity_readout (ONE k1_fused launch) at the config-2 maximum: HW=1620, 9 working + 5 permanent
-    frames.  An L2-sized buffer is rewritten between launches."""
+def k1_roofline(device, hw=1620, frames=(9, 5)):
+    """CUDA-event timing of xm_affinity_readout (ONE k1_fused launch) at a full memory: `frames` = (working, permanent) frames of
+    `hw` columns each — the config-2 maximum by default (HW=1620, 9 + 5 frames).  An L2-sized buffer is rewritten between launches."""
     from xmem2_b200.util import synth_memory as sm
-    hw, nw, npm = 1620, 9 * 1620, 5 * 1620
+    nw, npm = frames[0] * hw, frames[1] * hw
     case = sm.make_case(hw=hw, sizes=(0, nw, npm), n_obj=1, group_begins=[(0, 1, [0, 0, 0])], seed=11, device=device)
     a, keep = sm.device_args(case)
     out = torch.empty(1, hw, 512, dtype=torch.float16, device=device)
@@ -156,7 +156,8 @@ def k1_roofline(device):
     traffic, traffic_src = None, None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
         tj = json.load(open(os.path.join(REPO, 'profiles', 'r2_k1_traffic.json')))
-        traffic, traffic_src = tj['dram_bytes_per_launch'], tj.get('captured_at')
+        if hw == 1620:
+            traffic, traffic_src = tj['dram_bytes_per_launch'], tj.get('captured_at')
     except Exception:
         pass
     return {'bound': 'tensor', 'achieved': round(flops / t / 1e12, 2), 'peak': peak, 'unit': 'TFLOP/s',
@@ -165,6 +166,23 @@ def k1_roofline(device):
             'launch_us': round(t * 1e6, 1), 'shape': {'N': N, 'HW': hw, 'n_obj': 1},
             'peak_source': 'MEASURED_PEAKS.json bf16 burst' if peaks else 'fallback', 'algorithmic_bytes': bytes_,
             'hbm_gbs_if_bytes_bound': round(bytes_ / t / 1e9, 1)}
+
+
+def conv_roofline(device):
+    """The convolution family (K2+K4+K5 GEMM-shaped work): every conv shape of one ordinary 480p frame, graph-replayed and
+    CUDA-event timed per shape (xmem2_b200/util/conv_bench.py), summed with the per-frame multiplicities."""
+    from xmem2_b200.util.conv_bench import conv_table
+    rows, us, fl = conv_table(device)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = peaks.get('bf16_tflops', 1590.0)
+    top = sorted(rows, key=lambda r: -r['us'] * r['per_frame'])[:6]
+    return {'bound': 'tensor', 'achieved': round(fl / us / 1e6, 1), 'peak': peak, 'unit': 'TFLOP/s', 'frac': round(fl / us / 1e6 / peak, 4),
+            'frame_us': round(us, 1), 'frame_gflop': round(fl / 1e9, 1), 'launches': sum(r['per_frame'] for r in rows),
+            'kernels': 'conv_igemm_kernel (cluster split-K) / conv_pair_kernel (CTA pairs, BN=256) / conv3x3_c1', 'top_shapes': top}
 
 
 def oracle_clip(device, n_frames, threads=None, autocast=False, seed=1234, keep=None):
@@ -402,6 +420,12 @@ def main():
                 line['roofline'] = k1_roofline(device)
             except Exception as e:                       # never lose the headline number to the side measurement
                 line['roofline'] = {'error': str(e)[:200]}
+            try:   # the same kernel at the 1080p memory size (config 4: HW=8160, 6 working + 5 permanent frames)
+                r4 = k1_roofline(device, hw=8160, frames=(6, 5))
+                line['roofline_1080p_shape'] = {k: r4[k] for k in ('achieved', 'peak', 'unit', 'frac', 'launch_us', 'shape', 'algorithmic_bytes')}
+                line['conv_roofline'] = conv_roofline(device)
+            except Exception as e:
+                line['roofline_1080p_shape'] = {'error': str(e)[:200]}
             try:
                 nfr = cpu_sample_frames(cores)
                 ref_masks = []

@@ -14,7 +14,7 @@ T0 = float(sys.argv[2]) if len(sys.argv) > 2 else 3.5      # us
 MMA_FLOP_PER_US = 2.25e15 / SMS / 1e6                       # dense fp16 per SM
 
 h, w = 30, 54
-SHAPES = [  # (name, H, W, cin, cout, k, stride, count per frame) — tests/bench_conv.py
+SHAPES = [  # (name, H, W, cin, cout, k, stride, count per frame) — xmem2_b200/util/conv_bench.py
     ('stem 1x1 K192', 240, 432, 192, 64, 1, 1, 1), ('res2 1x1 64->64', 120, 216, 64, 64, 1, 1, 1),
     ('res2 3x3 64', 120, 216, 64, 64, 3, 1, 3), ('res2 1x1 64->256', 120, 216, 64, 256, 1, 1, 4),
     ('res2 1x1 256->64', 120, 216, 256, 64, 1, 1, 2), ('l2 1x1 256->128', 120, 216, 256, 128, 1, 1, 1),
