@@ -220,14 +220,31 @@ __global__ void cbam_pool_kernel(const __half* __restrict__ x, int HW, int C, fl
     }
 }
 // (b) scale_c = sigmoid(mlp(avg) + mlp(max)).  One block (C threads) per image; hidden width R = C/16.
-__global__ void cbam_mlp_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, int HW, const float* __restrict__ w1,
-                                const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int C,
-                                int R, float* __restrict__ scale) {
-    pdl_wait();
-    pdl_launch_dependents();
+// FAST = the fuser's shape (C = 512, R = 32, 512 threads): both weight matrices are pulled into registers BEFORE the
+// programmatic-dependency wait (they are constants, nothing upstream writes them), so the 128 KB of weight traffic overlaps the
+// pooling kernel's tail and the dependent part is two short reductions instead of a dozen serial memory round trips.
+template <bool FAST>
+__global__ void __launch_bounds__(512) cbam_mlp_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, int HW,
+                                const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                                const float* __restrict__ b2, int C, int R, float* __restrict__ scale) {
     extern __shared__ float sh[];          // [2][C] inputs, [2][R] hidden
     float* in0 = sh; float* in1 = sh + C; float* h0 = sh + 2 * C; float* h1 = h0 + R;
     const int b = blockIdx.x, t = threadIdx.x;
+    const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
+    float w1r[2][16]; float4 w2r[8]; float b1r[2], b2r = 0.f;
+    if (FAST) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) w1r[j][e] = __ldg(w1 + (size_t)(warp + 16 * j) * 512 + lane + 32 * e);
+            b1r[j] = __ldg(b1 + warp + 16 * j);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w2r[e] = __ldg(reinterpret_cast<const float4*>(w2 + (size_t)t * 32) + e);
+        b2r = __ldg(b2 + t);
+    }
+    pdl_wait();
+    pdl_launch_dependents();
     {
         float s = 0.f, m = -INFINITY;
 #pragma unroll
@@ -238,8 +255,30 @@ __global__ void cbam_mlp_kernel(const float* __restrict__ psum, const float* __r
         in0[t] = s / HW; in1[t] = m;
     }
     __syncthreads();
+    if (FAST) {
+        // warp w owns hidden units w and w+16 for BOTH pooled inputs (they share the weight row)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { a0 += w1r[j][e] * in0[lane + 32 * e]; a1 += w1r[j][e] * in1[lane + 32 * e]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+            if (lane == 0) { h0[warp + 16 * j] = fmaxf(a0 + b1r[j], 0.f); h1[warp + 16 * j] = fmaxf(a1 + b1r[j], 0.f); }
+        }
+        __syncthreads();
+        float a = 2.f * b2r;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            a += w2r[e].x * (h0[4 * e] + h1[4 * e]);
+            a += w2r[e].y * (h0[4 * e + 1] + h1[4 * e + 1]);
+            a += w2r[e].z * (h0[4 * e + 2] + h1[4 * e + 2]);
+            a += w2r[e].w * (h0[4 * e + 3] + h1[4 * e + 3]);
+        }
+        scale[(size_t)b * C + t] = sigmoidf_(a);
+        return;
+    }
     // hidden layer: one warp per (input, unit) pair, lanes stride over C
-    const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
     for (int u = warp; u < 2 * R; u += nwarps) {
         const int r = u % R; const float* in = (u < R) ? in0 : in1;
         float a = 0.f;
@@ -383,7 +422,7 @@ __global__ void area_down_kernel(const __half* __restrict__ in, const __half* __
 // ---------------------------------------------------------------- single-output 3x3 convolution (decoder.pred, modules.py:227,239)
 // logits[b][y][x] = bias + sum_{tap,c} w[tap][c] * in[b][y+dy][x+dx][c].  One block = 8x8 output pixels: the 10x10xC halo
 // tile is staged in shared memory once (instead of 9 L2 reads per pixel); one warp per output row, lanes split channels.
-__global__ void conv3x3_c1_kernel(const __half* __restrict__ in, const __half* __restrict__ wgt, float bias, int B, int H, int W, int C,
+__global__ void __launch_bounds__(256, 3) conv3x3_c1_kernel(const __half* __restrict__ in, const __half* __restrict__ wgt, float bias, int B, int H, int W, int C,
                                   __half* __restrict__ out) {
     pdl_wait();
     pdl_launch_dependents();
@@ -394,12 +433,33 @@ __global__ void conv3x3_c1_kernel(const __half* __restrict__ in, const __half* _
     const int tx = t % tiles_x; t /= tiles_x;
     const int ty = t % tiles_y; const int b = t / tiles_y;
     const int x0 = tx * 8 - 1, y0 = ty * 8 - 1;
-    for (int i = threadIdx.x; i < 100 * C8; i += blockDim.x) {
-        const int c8 = i % C8, px = (i / C8) % 10, py = i / (C8 * 10);
-        const int y = y0 + py, x = x0 + px;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * H + y) * W + x) * C) + c8);
-        tile_sm[i] = v;
+    if (C8 == 32 && blockDim.x == 256) {
+        // 100 halo pixels x 32 uint4: thread = (pixel slot, channel octet); the loads are issued in two batches of seven before
+        // their stores, so the fill costs two memory round trips instead of thirteen
+        const int c8 = threadIdx.x & 31, p0 = threadIdx.x >> 5;
+#pragma unroll 1
+        for (int j0 = 0; j0 < 14; j0 += 7) {
+            uint4 v[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const int pix = p0 + 8 * (j0 + j), py = pix / 10, px = pix - py * 10;
+                const int y = y0 + py, x = x0 + px;
+                v[j] = make_uint4(0u, 0u, 0u, 0u);
+                if (pix < 100 && y >= 0 && y < H && x >= 0 && x < W)
+                    v[j] = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * H + y) * W + x) * C) + c8);
+            }
+#pragma unroll
+            for (int j = 0; j < 7; ++j)
+                if (p0 + 8 * (j0 + j) < 100) tile_sm[(p0 + 8 * (j0 + j)) * 32 + c8] = v[j];
+        }
+    } else {
+        for (int i = threadIdx.x; i < 100 * C8; i += blockDim.x) {
+            const int c8 = i % C8, px = (i / C8) % 10, py = i / (C8 * 10);
+            const int y = y0 + py, x = x0 + px;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * H + y) * W + x) * C) + c8);
+            tile_sm[i] = v;
+        }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;       // 8 warps: warp = output row inside the patch
@@ -567,7 +627,10 @@ extern "C" int xm_cbam(const void* x, int32_t B, int32_t H, int32_t W, int32_t C
     float* avg = scratch; float* mx = avg + (size_t)B * CBAM_SLICES * C; float* scale = mx + (size_t)B * CBAM_SLICES * C;
     float* comp = scale + (size_t)B * C;
     XM_CHECK_CUDA(tc5_launch(cbam_pool_kernel, dim3(dim3(C / 64, B, CBAM_SLICES)), dim3(dim3(64, 4)), 0, STREAM, (const __half*)x, HW, C, avg, mx));
-    XM_CHECK_CUDA(tc5_launch(cbam_mlp_kernel, dim3(B), dim3(C), (2 * C + 2 * R) * sizeof(float), STREAM, avg, mx, HW, w1, b1, w2, b2, C, R, scale));
+    if (C == 512 && R == 32)
+        XM_CHECK_CUDA(tc5_launch(cbam_mlp_kernel<true>, dim3(B), dim3(C), (2 * C + 2 * R) * sizeof(float), STREAM, avg, mx, HW, w1, b1, w2, b2, C, R, scale));
+    else
+        XM_CHECK_CUDA(tc5_launch(cbam_mlp_kernel<false>, dim3(B), dim3(C), (2 * C + 2 * R) * sizeof(float), STREAM, avg, mx, HW, w1, b1, w2, b2, C, R, scale));
     const size_t npix = (size_t)B * HW;
     XM_CHECK_CUDA(tc5_launch(cbam_spatial_pool_kernel, dim3((unsigned)((npix + 7) / 8)), dim3(256), 0, STREAM, (const __half*)x, scale, B, HW, C, comp));
     XM_CHECK_CUDA(tc5_launch(cbam_apply_kernel, dim3((unsigned)((npix + 7) / 8)), dim3(256), 0, STREAM, (const __half*)x, scale, comp, w7, b7, B, H, W, C, (__half*)out,
