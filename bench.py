@@ -182,7 +182,7 @@ def conv_roofline(device):
     top = sorted(rows, key=lambda r: -r['us'] * r['per_frame'])[:6]
     return {'bound': 'tensor', 'achieved': round(fl / us / 1e6, 1), 'peak': peak, 'unit': 'TFLOP/s', 'frac': round(fl / us / 1e6 / peak, 4),
             'frame_us': round(us, 1), 'frame_gflop': round(fl / 1e9, 1), 'launches': sum(r['per_frame'] for r in rows),
-            'kernels': 'conv_igemm_kernel (cluster split-K) / conv_pair_kernel (CTA pairs, BN=256) / conv3x3_c1', 'top_shapes': top}
+            'kernels': 'conv_igemm_csk_kernel (cluster split-K) / conv_igemm_2cta_kernel (CTA pairs, BN=256) / conv3x3_c1_kernel', 'top_shapes': top}
 
 
 def oracle_clip(device, n_frames, threads=None, autocast=False, seed=1234, keep=None):

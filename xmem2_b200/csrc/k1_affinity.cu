@@ -210,7 +210,7 @@ struct SweepSmem {
     KStage st[P1_KSTAGES];                                   // merge scratch aliases this
 };
 struct ReadSmem {
-    alignas(1024) uint8_t v[P2_VSTAGES][256 * 128];          // [stage] 256 channel rows x (64 columns = 128 B); reduce scratch aliases this
+    alignas(1024) uint8_t v[P2_VSTAGES][256 * 128];          // [stage] 256 channel rows x (64 columns = 128 B)
     alignas(1024) uint8_t p[2][2][TQ * 128];                 // [buffer][q-tile] 128 query rows x (64 columns = 128 B)
     float entw[P2_MAXENT];                                   // weights of this item's entries, bucketed by k-tile
     uint16_t entp[P2_MAXENT];                                // their position in the P tile: q-tile << 13 | row << 6 | column
@@ -759,10 +759,13 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                         const int nval = S1 * 2 * NSLOT;
                         const float* src = p.candA + (size_t)q * nval;
                         float m1 = -INFINITY, m2 = -INFINITY;
-                        for (int u = lane; u < nval; u += 32) {
-                            const float v = __ldcg(src + u);
-                            m2 = fmaxf(m2, fminf(m1, v));
-                            m1 = fmaxf(m1, v);
+                        float cv[MAX_SLICE1 * 2 * NSLOT / 32];        // all loads in flight at once: one L2 round trip
+#pragma unroll
+                        for (int j = 0; j < MAX_SLICE1 * 2 * NSLOT / 32; ++j) cv[j] = (lane + 32 * j < nval) ? __ldcg(src + lane + 32 * j) : -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < MAX_SLICE1 * 2 * NSLOT / 32; ++j) {
+                            m2 = fmaxf(m2, fminf(m1, cv[j]));
+                            m1 = fmaxf(m1, cv[j]);
                         }
                         const uint32_t o1 = f2ord(m1), o2 = f2ord(m2);
                         uint32_t t = 0u;
@@ -892,6 +895,8 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                 }
             } else if (warp == 1) {
                 if (lane == 0) {
+                    // N = 256 on purpose: an M128 x N128 SS MMA re-reads the 4 KB P slice per 64 clocks of math (128 B/clk of
+                    // shared memory, the whole budget) -- splitting the value tile in two N = 128 halves was measured 1.5x slower
                     constexpr uint32_t idesc_o = make_idesc_f16(TQ, 256);
                     if (item_iter > 0) { mbar_wait(&cm.oempty, (item_iter - 1) & 1, 8); tc_fence_after(); }
                     for (int n = 0; n < nkt; ++n) {
@@ -916,16 +921,28 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                 // workers: bucket this CTA's (column, weight) entries by k-tile, then warps 0/1 build the P tiles
                 const int wt = threadIdx.x - 64;                // 0..511
                 int prev_b = 0, prev_e = 0;                     // builder: entries currently set in its P buffer
+                // this pair's final (column, weight) lists: 256 queries x 32 entries = 16 per worker thread, fetched in ONE
+                // batch of independent loads (a load-per-iteration loop around the shared-memory atomics below costs a
+                // serial L2 round trip per entry, twice)
+                constexpr int ENT_PER_THREAD = QPAIR * LISTK / (NWORK * 32);
+                uint2 ent[ENT_PER_THREAD];
+                {
+                    const uint2* fin = p.fin + (size_t)(rpair * QPAIR) * LISTK;
+#pragma unroll
+                    for (int j = 0; j < ENT_PER_THREAD; ++j) {
+                        const int i = wt + j * (NWORK * 32);
+                        ent[j] = (i < rnqh * TQ * LISTK) ? __ldcg(fin + i) : make_uint2(0xffffffffu, 0u);
+                    }
+                }
                 for (int kb = k0; kb < k1 || kb == k0; kb += P2_MAXKT) {
                     const int ke = min(k1, kb + P2_MAXKT), nb = ke - kb;
                     if (nb <= 0) break;
                     asm volatile("bar.sync 1, 512;" ::: "memory");     // previous batch's tables are no longer read
                     for (int i = wt; i <= nb; i += NWORK * 32) rd.cur[i] = 0u;
                     asm volatile("bar.sync 1, 512;" ::: "memory");
-                    const uint2* fin = p.fin + (size_t)(rpair * QPAIR) * LISTK;
-                    for (int i = wt; i < rnqh * TQ * LISTK; i += NWORK * 32) {
-                        const uint2 e = __ldcg(fin + i);
-                        const int kt = (e.x == 0xffffffffu) ? -1 : (int)(e.x >> 6);
+#pragma unroll
+                    for (int j = 0; j < ENT_PER_THREAD; ++j) {
+                        const int kt = (ent[j].x == 0xffffffffu) ? -1 : (int)(ent[j].x >> 6);
                         if (kt >= kb && kt < ke) atomicAdd(&rd.cur[kt - kb + 1], 1u);
                     }
                     asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -943,12 +960,13 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                     asm volatile("bar.sync 1, 512;" ::: "memory");
                     // cur[i] (i <= nb) now = number of entries in k-tiles < i ... shifted: counts were stored at index kt+1,
                     // so cur[kt] = first entry of k-tile kt and cur[kt + 1] = one past its last
-                    for (int i = wt; i < rnqh * TQ * LISTK; i += NWORK * 32) {
-                        const uint2 e = __ldcg(fin + i);
+#pragma unroll
+                    for (int j = 0; j < ENT_PER_THREAD; ++j) {
+                        const uint2 e = ent[j];
                         const int kt = (e.x == 0xffffffffu) ? -1 : (int)(e.x >> 6);
                         if (kt >= kb && kt < ke) {
                             const uint32_t pos = atomicAdd(&rd.cur[kt - kb], 1u);
-                            const int ql = i / LISTK;            // query inside the pair
+                            const int ql = (wt + j * (NWORK * 32)) / LISTK;            // query inside the pair
                             rd.entp[pos] = (uint16_t)(((uint32_t)(ql >> 7) << 13) | ((uint32_t)(ql & 127) << 6) | (e.x & 63u));
                             rd.entw[pos] = __uint_as_float(e.y);
                         }
@@ -1008,7 +1026,11 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                     const int quad = warp & 3, part = ww >> 2;    // part: q-tile (part >> 1), 128-column half (part & 1)
                     const int h = part >> 1, chh = part & 1;
                     if (h < rnqh) {
-                        float* dst = p.partial + (size_t)w * (QPAIR * 256) + (size_t)(h * TQ + quad * 32 + lane) * 256 + chh * 128;
+                        // partial tile layout = 512-byte UNITS: unit (((h*4+quad)*2+chh)*4+c)*8+j holds channels
+                        // chh*128+c*32+j*4..+3 of the 32 queries of one TMEM lane quadrant, lane-major, so every warp store is
+                        // one contiguous 512 bytes (a query-major tile made each 16-byte store its own cache line: ~14 us)
+                        float4* dst = reinterpret_cast<float4*>(p.partial + (size_t)w * (QPAIR * 256)) +
+                                      (size_t)(((h * 4 + quad) * 2 + chh) * 32) * 32 + lane;
 #pragma unroll 1
                         for (int c = 0; c < 4; ++c) {
                             uint32_t r[32];
@@ -1020,8 +1042,8 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                                 for (int j = 0; j < 32; ++j) r[j] = 0u;
                             }
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                __stcg(reinterpret_cast<uint4*>(dst + c * 32 + j), make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]));
+                            for (int j = 0; j < 8; ++j)
+                                __stcg(reinterpret_cast<uint4*>(dst + (c * 8 + j) * 32), make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
                         }
                     }
                     tc_fence_before();
@@ -1058,51 +1080,44 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                 int item0, nsl;
                 if (p.n_rows <= MAX_ROWS_TABLE) { item0 = cm.row_item0[row]; nsl = p.row_slices[row]; } else { item0 = row; nsl = 1; }
                 const float* pbase = p.partial + (size_t)item0 * (QPAIR * 256);
-                // (1) NHWC outputs: one warp per (query, 128-channel quarter), a lane sums 4 channels over the slices
-                //     (independent 16-byte loads, 512 contiguous bytes per warp and slice)
-                for (int v = v0; v < rnqh * TQ * 2; v += vstride) {
-                    const int ql = v >> 1, cq = chalf * 2 + (v & 1);
-                    const int q = rpair * QPAIR + ql;
-                    const float4* src = reinterpret_cast<const float4*>(pbase + (size_t)ql * 256 + (v & 1) * 128) + lane;
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                // one warp per GROUP = 4 units = (32 queries of a lane quadrant) x (16 channels): a lane owns one query, sums
+                // 4 float4 per slice (512 contiguous bytes per warp load) and writes every requested output layout
+                for (int gi = v0; gi < rnqh * 64; gi += vstride) {
+                    const int jh = gi & 1, c = (gi >> 1) & 3, chh = (gi >> 3) & 1, quad = (gi >> 4) & 3, h = gi >> 6;
+                    const float4* src = reinterpret_cast<const float4*>(pbase) +
+                                        (size_t)((((h * 4 + quad) * 2 + chh) * 4 + c) * 8 + jh * 4) * 32 + lane;
+                    float4 acc[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
                     for (int s = 0; s < nsl; ++s) {
-                        const float4 f = __ldcg(src + (size_t)s * (QPAIR * 256 / 4));
-                        acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 f = __ldcg(src + (size_t)s * (QPAIR * 256 / 4) + j * 32);
+                            acc[j].x += f.x; acc[j].y += f.y; acc[j].z += f.z; acc[j].w += f.w;
+                        }
                     }
-                    const int c = cq * 128 + lane * 4;
+                    const int q = rpair * QPAIR + h * TQ + quad * 32 + lane;
+                    const int c0 = chalf * 256 + chh * 128 + c * 32 + jh * 16;
                     if (p.out_hwc && q < p.hw) {
-                        uint2 o;
-                        o.x = pack_half2(acc.x, acc.y); o.y = pack_half2(acc.z, acc.w);
-                        *reinterpret_cast<uint2*>(p.out_hwc + ((size_t)(p.obj_begin + obj) * p.hw + q) * XM_CV + c) = o;
+                        uint4* o = reinterpret_cast<uint4*>(p.out_hwc + ((size_t)(p.obj_begin + obj) * p.hw + q) * XM_CV + c0);
+                        o[0] = make_uint4(pack_half2(acc[0].x, acc[0].y), pack_half2(acc[0].z, acc[0].w), pack_half2(acc[1].x, acc[1].y), pack_half2(acc[1].z, acc[1].w));
+                        o[1] = make_uint4(pack_half2(acc[2].x, acc[2].y), pack_half2(acc[2].z, acc[2].w), pack_half2(acc[3].x, acc[3].y), pack_half2(acc[3].z, acc[3].w));
                     }
-                    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + ((size_t)obj * p.hw_pad + q) * XM_CV + c) = acc;
-                }
-                // (2) reference layout [object][channel][query] (tests, drop-in callers): 32 x 32 tiles transposed through smem
-                if (p.out_chw) {
-                    float* tr = reinterpret_cast<float*>(&rd.v[0][0]) + (size_t)ww * 32 * 33;
-                    for (int t = v0; t < rnqh * 4 * 8; t += vstride) {
-                        const int qb = t >> 3, cb = t & 7;
-                        const int ql0 = qb * 32, c0 = chalf * 256 + cb * 32;
-                        const int q0 = rpair * QPAIR + ql0;
-                        const float* src = pbase + (size_t)ql0 * 256 + cb * 32 + lane;
-                        float acc[32];
+                    if (p.out_f32) {
+                        float4* o = reinterpret_cast<float4*>(p.out_f32 + ((size_t)obj * p.hw_pad + q) * XM_CV + c0);
 #pragma unroll
-                        for (int qq = 0; qq < 32; ++qq) acc[qq] = 0.f;
-                        for (int sl = 0; sl < nsl; ++sl) {
+                        for (int j = 0; j < 4; ++j) o[j] = acc[j];
+                    }
+                    if (p.out_chw && q < p.hw) {       // reference layout [object][channel][query]: lanes are consecutive queries
+                        __half* o = p.out_chw + ((size_t)(p.obj_begin + obj) * XM_CV + c0) * p.hw + q;
 #pragma unroll
-                            for (int qq = 0; qq < 32; ++qq) acc[qq] += __ldcg(src + (size_t)sl * (QPAIR * 256) + qq * 256);
+                        for (int j = 0; j < 4; ++j) {
+                            o[(size_t)(4 * j + 0) * p.hw] = __float2half_rn(acc[j].x);
+                            o[(size_t)(4 * j + 1) * p.hw] = __float2half_rn(acc[j].y);
+                            o[(size_t)(4 * j + 2) * p.hw] = __float2half_rn(acc[j].z);
+                            o[(size_t)(4 * j + 3) * p.hw] = __float2half_rn(acc[j].w);
                         }
-#pragma unroll
-                        for (int qq = 0; qq < 32; ++qq) tr[qq * 33 + lane] = acc[qq];
-                        __syncwarp();
-                        const int q = q0 + lane;
-                        if (q < p.hw) {
-#pragma unroll 4
-                            for (int cc = 0; cc < 32; ++cc)
-                                p.out_chw[((size_t)(p.obj_begin + obj) * XM_CV + c0 + cc) * p.hw + q] = __float2half_rn(tr[lane * 33 + cc]);
-                        }
-                        __syncwarp();
                     }
                 }
             };
