@@ -50,7 +50,7 @@ for rep in range(3):
     buf = np.zeros((160, 16), dtype=np.uint64)
     n = L.xm_affinity_debug_timeline(ws.data_ptr(), hw, n_obj, buf.ctypes.data, 160)
     t = buf[:n, :11].astype(np.int64)
-    tb = buf[:n, 11:15].astype(np.int64)
+    tb = buf[:n, 11:16].astype(np.int64)
     t0 = t[:, 0].min()
     if rep < 2 or True and rep < 2:
         continue
@@ -65,10 +65,17 @@ L.xm_affinity_debug_counts.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_voi
 L.xm_affinity_debug_counts(ws.data_ptr(), hw, n_obj, cnts.ctypes.data)
 print(f'candidates per query after sweep B: mean {cnts.mean():.1f}, median {np.median(cnts):.0f}, max {cnts.max()}, min {cnts.min()}')
 t0 = t[:, 0].min()
-print('first grid barrier, per CTA (us since start): arrive, after fence, after atomic, released  [sorted by arrival, every 12th]')
-order = np.argsort(t[:, 6])
-for c in list(order[::12]) + [order[-1]]:
-    print(f'  cta {c:3d}: stamp6 {(t[c,6]-t0)/1e3:7.1f} | sync {(tb[c,0]-t0)/1e3:7.1f} fence {(tb[c,1]-t0)/1e3:7.1f} atomic {(tb[c,2]-t0)/1e3:7.1f} seen {(tb[c,3]-t0)/1e3:7.1f} | stamp7 {(t[c,7]-t0)/1e3:7.1f}')
+rel = lambda x: (x - t0) / 1e3
+sw_ctas = t[:, 5] > 0
+print(f'merge B (worker stamp 11) ends: median {np.median(rel(tb[sw_ctas, 0])):.1f} max {rel(tb[sw_ctas, 0]).max():.1f} | barrier 3 released (stamp 5) median {np.median(rel(t[sw_ctas, 5])):.1f}')
+print('readout detail per CTA (us): tables built - barrier released | MMAs done - tables built | drained - MMAs done | stamp 8 - drained')
+d1, d2, d3, d4 = (tb[:, 1] - t[:, 7]) / 1e3, (tb[:, 2] - tb[:, 1]) / 1e3, (tb[:, 3] - tb[:, 2]) / 1e3, (t[:, 8] - tb[:, 3]) / 1e3
+d0 = (tb[:, 4] - t[:, 7]) / 1e3
+for nm, d in (('counted', d0), ('tables', d1), ('mma', d2), ('drain', d3), ('tail', d4)):
+    print(f'  {nm:8s} median {np.median(d):6.1f}  min {d.min():6.1f}  max {d.max():6.1f}')
+order = np.argsort(d2)
+print('  slowest MMA phases (cta, us):', [(int(c), round(float(d2[c]), 1)) for c in order[-8:]], ' fastest:', [(int(c), round(float(d2[c]), 1)) for c in order[:6]])
+print('  MMA phase by CTA index (every 4th):', [round(float(x), 1) for x in d2[::4]])
 if os.environ.get('K1_TRACE'):
     # cycle accounting of CTA 0 (library built with -DK1_TRACE)
     L.xm_affinity_debug_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]

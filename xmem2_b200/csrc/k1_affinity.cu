@@ -154,6 +154,9 @@ __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t
 #define K1_TRACE_OUT(slot, sweep, c0, c1, c2) do { } while (0)
 #endif
 #define K1_STAMP(i) do { if (threadIdx.x == 0) p.timeline[(size_t)blockIdx.x * 16 + (i)] = global_ns(); } while (0)
+// the same from the first worker thread (warp 2, lane 0): stamps 11..15 = merge B done, readout tables built, MMAs done, tile
+// drained, list entries counted
+#define K1_WSTAMP(i) do { if (threadIdx.x == 64) p.timeline[(size_t)blockIdx.x * 16 + (i)] = global_ns(); } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // operand packing
@@ -216,7 +219,6 @@ struct ReadSmem {
     uint16_t entp[P2_MAXENT];                                // their position in the P tile: q-tile << 13 | row << 6 | column
     uint32_t cur[P2_MAXKT + 1];
     uint16_t off[P2_MAXKT + 2];
-    unsigned long long utile[2][TK];                         // per builder: fixed-point column sums of the current k-tile
 };
 struct CommonSmem {
     alignas(8) uint64_t qfull;
@@ -245,14 +247,11 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 // Barrier among the CTAs that increment `ctr` (all co-resident: one CTA per SM, grid <= #SMs).  Bounded: a protocol bug or a
 // CTA that never became resident traps instead of hanging the GPU.
-__device__ void cta_group_barrier(unsigned* ctr, unsigned target, int tag, unsigned long long* stamps = nullptr) {
+__device__ void cta_group_barrier(unsigned* ctr, unsigned target, int tag) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (stamps) stamps[11] = global_ns();
         __threadfence();
-        if (stamps) stamps[12] = global_ns();
         atomicAdd(ctr, 1u);
-        if (stamps) stamps[13] = global_ns();
         unsigned long long t0 = 0ull;
         while (ld_acquire_u32(ctr) < target) {
             __nanosleep(40);
@@ -260,7 +259,6 @@ __device__ void cta_group_barrier(unsigned* ctr, unsigned target, int tag, unsig
             if (t0 == 0ull) t0 = now;
             if (now - t0 > 4000000000ull) mbar_timeout(tag, target);      // 4 s: a CTA never arrived
         }
-        if (stamps) stamps[14] = global_ns();
         __threadfence();
     }
     __syncthreads();
@@ -369,18 +367,18 @@ __device__ int warp_gather_lists(const K1Params& p, int q, uint64_t* scr, int ke
     int n = 0;
     if (total <= SCR_CAP) {
         const int off0 = x0 - c0, off1 = tot0 + x1 - c1;
-        // loads in batches of 4 per list (independent L2 requests in flight), then the shared-memory stores
+        // loads in batches of 8 per list (independent L2 requests in flight), then the shared-memory stores
         const uint2* l0 = lbase + (size_t)lane * LCAP;
         const uint2* l1 = lbase + (size_t)(lane + 32) * LCAP;
-        for (int e0 = 0; e0 < max(c0, c1); e0 += 4) {
-            uint2 a[4], b[4];
+        for (int e0 = 0; e0 < max(c0, c1); e0 += 8) {
+            uint2 a[8], b[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 a[u] = (e0 + u < c0) ? __ldcg(l0 + e0 + u) : make_uint2(0u, 0u);
                 b[u] = (e0 + u < c1) ? __ldcg(l1 + e0 + u) : make_uint2(0u, 0u);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 if (e0 + u < c0) scr[off0 + e0 + u] = make_key(a[u].x, a[u].y);
                 if (e0 + u < c1) scr[off1 + e0 + u] = make_key(b[u].x, b[u].y);
             }
@@ -690,9 +688,6 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                                   t > 0.f ? __float_as_uint(t) - 1u : (t < 0.f ? __float_as_uint(t) + 1u : 0x80000001u)));   // pred(tau_lo)
                     }
                     cx.glist = p.lists + (((size_t)q * S1 + slice) * 2 + b) * LCAP;          // this thread's candidate list
-#ifdef K1_NOHIT
-                    if (sweep == 1) cx.thr = FLT_MAX;      // experiment: cost of sweep B without any candidate
-#endif
                     long long c_wait = 0, c_scan = 0;
                     const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16) + (h * 2 + b) * TN;
                     for (int i = b; i < n_it; i += 2) {
@@ -844,6 +839,7 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
             K1_ACC(c_r, tw);
             if (lane == 0) K1_TRACE_OUT(18 + ww, 0, c_g, c_k, c_r);
         }
+        K1_WSTAMP(11);
     }
 
     // ------------------------------------------------------------------ readout: O[q, c] += P[q, n] V[n, c]
@@ -851,17 +847,17 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
         fence_proxy_async_smem();                             // the merge scratch (generic proxy) aliases the TMA / UMMA buffers below
         __syncthreads();
         K1_STAMP(6);
-        cta_group_barrier(p.ctr, ++grid_uses * G, 43, p.timeline + (size_t)blockIdx.x * 16);
-        K1_STAMP(7);
-        pdl_launch_dependents();
-        const int KT = sg.t64[sg.nseg];
-        // zero both P buffers once; afterwards only the listed entries are written and cleared again
+        // zero both P buffers once (the merge scratch they alias is dead after the barrier above); afterwards only the listed
+        // entries are written and cleared again.  Done while waiting for the other CTAs.
         if (warp >= 2) {
             uint4* pz = reinterpret_cast<uint4*>(&rd.p[0][0][0]);
             for (int i = threadIdx.x - 64; i < (int)(sizeof(rd.p) / 16); i += NWORK * 32) pz[i] = make_uint4(0u, 0u, 0u, 0u);
             fence_proxy_async_smem();
         }
-        __syncthreads();
+        cta_group_barrier(p.ctr, ++grid_uses * G, 43);
+        K1_STAMP(7);
+        pdl_launch_dependents();
+        const int KT = sg.t64[sg.nseg];
         int g0 = 0;                                           // running k-tile count of this CTA (mbarrier phases)
         int item_iter = 0;
         for (int w = cta; w < p.n_items; w += G, ++item_iter) {
@@ -946,6 +942,7 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                         if (kt >= kb && kt < ke) atomicAdd(&rd.cur[kt - kb + 1], 1u);
                     }
                     asm volatile("bar.sync 1, 512;" ::: "memory");
+                    if (item_iter == 0 && kb == k0) K1_WSTAMP(15);
                     if (ww == 0) {                               // exclusive scan of the counts (one warp)
                         uint32_t carry = 0u;
                         for (int b0 = 0; b0 <= nb; b0 += 32) {
@@ -972,9 +969,9 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                         }
                     }
                     asm volatile("bar.sync 1, 512;" ::: "memory");
+                    if (item_iter == 0 && kb == k0) K1_WSTAMP(12);
                     if (ww < 2) {
                         const int pb = ww;
-                        const bool usage_item = want_usage && chalf == 0 && obj == 0;     // one CTA per (query pair, k-tile) sums the usage
                         auto p_addr = [&](uint32_t x) -> uint16_t* {        // element (q-tile, row, column) of the swizzled P tile
                             const uint32_t r = (x >> 6) & 127u, c = x & 63u;
                             return reinterpret_cast<uint16_t*>(&rd.p[pb][(x >> 13) & 1u][r * 128 + (((c >> 3) ^ (r & 7u)) << 4) + (c & 7u) * 2]);
@@ -985,19 +982,6 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                             const int use = g >> 1;
                             const int li = (k0 + n) - kb;
                             const int eb = rd.off[li], ee = rd.off[li + 1];
-                            if (usage_item) {
-                                // column sums of this (query pair, k-tile) in 2^-40 fixed point: integer adds commute, so the
-                                // result does not depend on the order in which the entries were bucketed
-                                unsigned long long* ut = rd.utile[pb];
-                                ut[lane] = 0ull; ut[lane + 32] = 0ull;
-                                __syncwarp();
-                                for (int e = eb + lane; e < ee; e += 32)
-                                    atomicAdd(&ut[rd.entp[e] & 63u], (unsigned long long)(rd.entw[e] * 1099511627776.f));
-                                __syncwarp();
-                                unsigned long long* ua = p.uacc + (size_t)(k0 + n) * TK;
-                                if (ut[lane]) atomicAdd(ua + lane, ut[lane]);
-                                if (ut[lane + 32]) atomicAdd(ua + lane + 32, ut[lane + 32]);
-                            }
                             mbar_wait(&cm.pempty[pb], (use & 1) ^ 1, 11);
                             for (int e = prev_b + lane; e < prev_e; e += 32) *p_addr(rd.entp[e]) = 0;      // clear the previous use of this buffer
                             for (int e = eb + lane; e < ee; e += 32) *p_addr(rd.entp[e]) = __half_as_ushort(__float2half_rn(rd.entw[e]));
@@ -1018,10 +1002,31 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                             prev_b = prev_e = 0;
                         }
                     }
+                    else if (want_usage && chalf == 0 && obj == 0) {
+                        // usage (one CTA per (query pair, k-tile)): the 14 warps that do not build P tiles share the k-tiles.  A
+                        // lane owns columns lane and lane + 32 of the tile and walks the tile's (few) entries: column sums in
+                        // 2^-40 fixed point, no shared-memory atomics, and integer adds commute, so the result does not depend on
+                        // the order in which the entries were bucketed.  Off the P builders' critical path.
+                        for (int n = kb - k0 + (ww - 2); n < ke - k0; n += NWORK - 2) {
+                            const int li = (k0 + n) - kb;
+                            const int eb = rd.off[li], ee = rd.off[li + 1];
+                            unsigned long long a0 = 0ull, a1 = 0ull;
+                            for (int e = eb; e < ee; ++e) {
+                                const uint32_t c = rd.entp[e] & 63u;
+                                const unsigned long long wq = (unsigned long long)(rd.entw[e] * 1099511627776.f);
+                                if (c == (uint32_t)lane) a0 += wq;
+                                if (c == (uint32_t)lane + 32u) a1 += wq;
+                            }
+                            unsigned long long* ua = p.uacc + (size_t)(k0 + n) * TK;
+                            if (a0) atomicAdd(ua + lane, a0);
+                            if (a1) atomicAdd(ua + lane + 32, a1);
+                        }
+                    }
                 }
                 // epilogue: O (2 x 128 lanes x 256 columns fp32) -> this item's partial tile
                 mbar_wait(&cm.ofull, item_iter & 1, 13);
                 tc_fence_after();
+                K1_WSTAMP(13);
                 {
                     const int quad = warp & 3, part = ww >> 2;    // part: q-tile (part >> 1), 128-column half (part & 1)
                     const int h = part >> 1, chh = part & 1;
@@ -1049,6 +1054,7 @@ k1_fused(const __grid_constant__ K1Maps maps, const __grid_constant__ K1Params p
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&cm.oempty);
+                    K1_WSTAMP(14);
                 }
             }
             g0 += nkt;
@@ -1393,7 +1399,9 @@ void k1_plan_items(const K1Geom& g, int n_obj, K1Params& p) {
     int weight[MAX_ROWS_TABLE]; int wsum = 0;
     for (int r = 0; r < p.n_rows; ++r) {
         const int rpair = (r >> 1) / n_obj;
-        weight[r] = (rpair * 2 + 1 < g.qtiles) ? 2 : 1;
+        // cost of a k-tile: a whole pair is bound by its two M128 x N256 MMAs (~0.56 us), the trailing half pair by the 32 KB
+        // value tile every CTA has to pull through TMA whatever it multiplies it with (~0.5 us) -- measured, not 2 : 1
+        weight[r] = (rpair * 2 + 1 < g.qtiles) ? 16 : 14;
         wsum += weight[r];
     }
     int given = 0;
