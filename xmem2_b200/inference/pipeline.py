@@ -28,7 +28,10 @@ class MaskDownloader:
         self.table = label_table
         self.depth = depth
         self.host = [torch.empty(self.shape, dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self.dev = [torch.empty(self.shape, dtype=torch.uint8, device=self.device) for _ in range(depth)]
         self.events = [torch.cuda.Event() for _ in range(depth)]
+        self.labelled = [torch.cuda.Event() for _ in range(depth)]
+        self.stream = torch.cuda.Stream(device=self.device)      # device -> host copies run beside the next frame's kernels
         self.pending = deque()          # (frame index, slot)
         self.n = 0
         self.bytes_per_frame = self.shape[0] * self.shape[1]
@@ -40,9 +43,13 @@ class MaskDownloader:
             out.append(self._pop())
         slot = self.n % self.depth
         self.n += 1
-        labels = post_process(prob, self.shape, self.table)
-        self.host[slot].copy_(labels, non_blocking=True)
-        self.events[slot].record()
+        # slot's device buffer is free: its previous copy was waited for when the slot was popped
+        post_process(prob, self.shape, self.table, out=self.dev[slot])
+        self.labelled[slot].record()
+        self.stream.wait_event(self.labelled[slot])
+        with torch.cuda.stream(self.stream):
+            self.host[slot].copy_(self.dev[slot], non_blocking=True)
+            self.events[slot].record(self.stream)
         self.pending.append((frame_index, slot))
         return out
 

@@ -28,14 +28,18 @@ def label_table(remappings: dict) -> torch.Tensor:
     return t
 
 
-def post_process(prob: torch.Tensor, shape: Optional[Sequence[int]] = None, label_table: Optional[torch.Tensor] = None) -> torch.Tensor:
+def post_process(prob: torch.Tensor, shape: Optional[Sequence[int]] = None, label_table: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """prob [n_obj+1, H, W] fp32 (a strided view is fine as long as the last stride is 1) -> uint8 [shape] index mask on
-    the same device.  `shape=None` keeps H x W (the `need_resize == False` branch of the reference)."""
+    the same device.  `shape=None` keeps H x W (the `need_resize == False` branch of the reference).  `out`: optional uint8 [shape]
+    device buffer to write into (callers that overlap the download with the next frame own a ring of them)."""
     lib.require_cuda(prob, 'prob')
     assert prob.dim() == 3 and prob.dtype == torch.float32 and prob.stride(2) == 1
     c, h, w = prob.shape
     oh, ow = (h, w) if shape is None else (int(shape[0]), int(shape[1]))
-    out = torch.empty((oh, ow), dtype=torch.uint8, device=prob.device)
+    if out is None:
+        out = torch.empty((oh, ow), dtype=torch.uint8, device=prob.device)
+    assert out.is_cuda and out.dtype == torch.uint8 and tuple(out.shape) == (oh, ow) and out.is_contiguous()
     lut = None
     if label_table is not None:
         lut = label_table.to(device=prob.device, dtype=torch.uint8).contiguous()
