@@ -1,6 +1,6 @@
 """Back-of-the-envelope model of the convolution kernel (no GPU needed): replays the host tile plan of
 csrc/conv_igemm.cu for every convolution shape of a 480p frame and predicts its time from ONE measured constant, the
-bytes per second an SM pulls through its L2 port (ROUND1_NOTES.md: ~70 GB/s per active SM, from the ncu launch list),
+bytes per second an SM pulls through its L2 port (NOTES.md: ~70 GB/s per active SM, from the ncu launch list),
 plus a fixed launch/prologue/epilogue cost.  Then predicts what the experimental variants would buy:
   csk  : cluster split-K (2-3 CTAs per output tile, DSMEM fix-up ~1.5 us) for grids that leave SMs idle
   2cta : CTA pairs, M=256, each CTA loads half of the weight tile (BN=128 or 256)

@@ -1,5 +1,5 @@
 // tma_ingest.cu — how many bytes per second can ONE SM pull from L2 through TMA, and how does that scale with the number of
-// active SMs, CTAs per SM and 2-CTA multicast?  (ROUND1_NOTES.md: the convolutions look bound by ~65-70 GB/s per active SM;
+// active SMs, CTAs per SM and 2-CTA multicast?  (NOTES.md: the convolutions look bound by ~65-70 GB/s per active SM;
 // this settles whether small grids should be spread over more SMs (cluster split-K) and whether multicast helps at all.)
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tma_ingest tma_ingest.cu -lcuda && ./tma_ingest

@@ -12,7 +12,7 @@
 //   leader: own TMEM + partial[0] (+ partial[1]) -> bias / residual / ReLU -> TMA store (or the plain store path)
 // Layers that fill more than one wave of 128x128 tiles but fit one wave of CTA pairs go to conv_igemm_pair.cu
 // (cta_group::2, M = 256, each CTA loads half of the weight tile: half the bytes per FLOP through each SM's TMA).
-// Measured on B200 (round 2, tests/bench_conv.py): 905 -> 853 us per 480p frame against the round-1 kernel with its global
+// Measured on B200 (round 2, python -m xmem2_b200.util.conv_bench): 905 -> 853 us per 480p frame against the round-1 kernel with its global
 // split-K; the pair kernel takes the 60x108 512->512 decoder convolution from 57 to 32 us.
 //
 // conv_igemm.cu — implicit-GEMM convolution on tcgen05 for NHWC fp16 activations.

@@ -1,4 +1,4 @@
-// conv_igemm_2cta.cu — the production implicit-GEMM convolution (../conv_igemm.cu) on CTA PAIRS (tcgen05 cta_group::2):
+// conv_igemm_pair.cu — the production implicit-GEMM convolution (../conv_igemm.cu) on CTA PAIRS (tcgen05 cta_group::2):
 // two CTAs of a cluster (2,1,1) own two neighbouring 128-pixel tiles and the SAME BN output channels; the leader issues
 // one M=256 x N=BN MMA per 16 channels that reads A (128 pixel rows) from each CTA's own shared memory and B from BOTH
 // (each CTA holds BN/2 weight rows), and writes each CTA's 128 x BN accumulator into that CTA's TMEM.  Per K-step an SM
@@ -7,7 +7,7 @@
 //     here    BN=128       : 24 KB per 2.1 MFLOP per SM   (1.33x)
 //             BN=256       : 32 KB per 4.2 MFLOP per SM   (2x)
 // which is what the layers that fill the machine need: they are bound by the ~65-90 GB/s an SM can pull from L2
-// (ROUND1_NOTES.md).  Protocol (the one CUTLASS' sm100 2SM pipeline uses):
+// (NOTES.md).  Protocol (the one CUTLASS' sm100 2SM pipeline uses):
 //   * TMEM is allocated/freed with cta_group::2 by warp 1 of BOTH CTAs; cluster barrier after the barrier init and
 //     before the free;
 //   * both producers wait on their OWN empty[s] and issue `cp.async.bulk.tensor ... .cta_group::2` loads into their own
@@ -18,7 +18,7 @@
 //   * each CTA runs the normal epilogue on its own TMEM lanes (bias / residual / ReLU / TMA store).
 // No split-K here.  cout_pad must be a multiple of BN (128 or 256).  An odd number of pixel tiles is padded with a CTA
 // whose loads are zero-filled (batch coordinate out of range) and whose stores are clipped.
-// Compile check:  nvcc -gencode arch=compute_100a,code=sm_100a -c conv_igemm_2cta.cu
+// Compile check:  nvcc -gencode arch=compute_100a,code=sm_100a -c conv_igemm_pair.cu
 //
 // conv_igemm.cu — implicit-GEMM convolution on tcgen05 for NHWC fp16 activations.
 //
