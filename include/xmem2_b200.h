@@ -154,6 +154,15 @@ int xm_conv2d_nhwc(const xm_conv_args_t* args, void* stream);
  * out fp16 [n][H/2][W/2][kpad], k = (kh*7+kw)*C + c with C = 3 (image) or 5 (image, mask_b, sum of other masks):
  * model/resnet.py:120 and ValueEncoder.forward model/modules.py:124-135.                                 */
 int xm_im2col_stem(const float* image, const float* masks, int32_t n, int32_t H, int32_t W, int32_t kpad, void* out, void* stream);
+/* Fused 7x7 / stride-2 stem convolution (+ folded BatchNorm, optional ReLU): the im2col tile is built in shared memory and
+ * multiplied on tcgen05 in the same kernel (replaces xm_im2col_stem + a 1x1 xm_conv2d_nhwc on the inference path).
+ * Reference: `self.conv1(f)` + `bn1` (+ `relu`) of KeyEncoder (model/modules.py:165-168, model/resnet.py:120) and of ValueEncoder
+ * after `torch.cat([image, mask, others], 1)` (model/modules.py:124-137).
+ * image fp32 [3][H][W]; masks fp32 [n][H][W] or NULL.  masks == NULL: 3 input channels, n = 1, kpad = 192, K index
+ * kh*24 + kw*3 + c; otherwise 5 channels (image, mask[b], sum of the other masks), kpad = 256, K index (kh*7+kw)*5 + c.
+ * weight fp16 [64][kpad], bias fp32 [64]; out fp16 NHWC [n][H/2][W/2][64]. */
+int xm_stem7x7(const float* image, const float* masks, int32_t n, int32_t H, int32_t W, const void* weight, const float* bias,
+               int32_t kpad, int32_t relu, void* out, void* stream);
 /* nn.MaxPool2d(3, 2, 1) on NHWC fp16; relu != 0 applies ReLU after the pool (modules.py:137-138).        */
 int xm_maxpool3x3s2(const void* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t relu, void* out, void* stream);
 int xm_relu(const void* in, void* out, int64_t n, void* stream);

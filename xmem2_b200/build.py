@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libxmem2_b200.so')
-SOURCES = ['common.cu', 'k1_affinity.cu', 'conv_igemm.cu', 'conv_igemm_pair.cu', 'pair_dissim.cu', 'consolidate.cu', 'eltwise.cu', 'postproc.cu']
+SOURCES = ['common.cu', 'k1_affinity.cu', 'conv_igemm.cu', 'conv_igemm_pair.cu', 'pair_dissim.cu', 'consolidate.cu', 'eltwise.cu', 'stem7x7.cu', 'postproc.cu']
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math',
          '-Xcompiler', '-fPIC', '-cudart', 'static'] + os.environ.get('XMEM_EXTRA_NVCC_FLAGS', '').split()
 

@@ -85,6 +85,7 @@ def load() -> C.CDLL:
         lib.xm_launch_count.restype = C.c_longlong
         lib.xm_add_launch_count.argtypes = [C.c_int]
         lib.xm_im2col_stem.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+        lib.xm_stem7x7.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, i32, vp, vp]
         lib.xm_maxpool3x3s2.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
         lib.xm_relu.argtypes = [vp, vp, i64, vp]
         lib.xm_keyproj_post.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]

@@ -244,9 +244,7 @@ class XMem(nn.Module):
         self._ensure_packed(dev)
         L = lib.load()
         img = frame[0].float().contiguous()
-        col = torch.empty((1, H // 2, W // 2, 192), dtype=torch.float16, device=dev)
-        lib.check(L.xm_im2col_stem(img.data_ptr(), None, 1, H, W, 192, col.data_ptr(), lib.stream_ptr()), 'xm_im2col_stem')
-        x = self._conv('key_encoder.conv1', [(col, False)], relu=True)
+        x = self._stem('key_encoder.conv1', img, None, 1, H, W, relu=True)
         p = torch.empty((1, H // 4, W // 4, 64), dtype=torch.float16, device=dev)
         lib.check(L.xm_maxpool3x3s2(x.data_ptr(), 1, H // 2, W // 2, 64, 0, p.data_ptr(), lib.stream_ptr()), 'xm_maxpool3x3s2')
         x = p
@@ -272,6 +270,15 @@ class XMem(nn.Module):
         return (_nchw_view(key), _nchw_view(shr) if need_sk else None, _nchw_view(sel) if need_ek else None,
                 _nchw_view(f16), _nchw_view(f8), _nchw_view(f4))
 
+    def _stem(self, name, img, masks, n, H, W, relu):
+        """7x7/s2 stem conv + folded bn (+relu) as one kernel (csrc/stem7x7.cu); img fp32 [3,H,W], masks fp32 [n,H,W] or None."""
+        wp, bp, cout, _ = self._pk[name]
+        assert cout == 64 and wp.shape[0] == 64
+        out = torch.empty((n, H // 2, W // 2, 64), dtype=torch.float16, device=img.device)
+        lib.check(lib.load().xm_stem7x7(img.data_ptr(), masks.data_ptr() if masks is not None else None, n, H, W, wp.data_ptr(),
+                                        bp.data_ptr(), wp.shape[1], 1 if relu else 0, out.data_ptr(), lib.stream_ptr()), 'xm_stem7x7')
+        return out
+
     def encode_value(self, frame, image_feat_f16, h16, masks, is_deep_update=True):
         """reference network.py:72-85 + ValueEncoder.forward modules.py:124-150.  masks [1,n,H,W]."""
         lib.require_cuda(frame, 'frame')
@@ -281,9 +288,7 @@ class XMem(nn.Module):
         _, n, H, W = masks.shape
         img = frame[0].float().contiguous()
         mk = masks[0].float().contiguous()
-        col = torch.empty((n, H // 2, W // 2, 256), dtype=torch.float16, device=dev)
-        lib.check(L.xm_im2col_stem(img.data_ptr(), mk.data_ptr(), n, H, W, 256, col.data_ptr(), lib.stream_ptr()), 'xm_im2col_stem')
-        x = self._conv('value_encoder.conv1', [(col, False)])               # conv + bn, no relu yet
+        x = self._stem('value_encoder.conv1', img, mk, n, H, W, relu=False)  # conv + bn, no relu yet
         p = torch.empty((n, H // 4, W // 4, 64), dtype=torch.float16, device=dev)
         lib.check(L.xm_maxpool3x3s2(x.data_ptr(), n, H // 2, W // 2, 64, 1, p.data_ptr(), lib.stream_ptr()), 'xm_maxpool3x3s2')
         x = p
