@@ -287,15 +287,24 @@ __device__ __forceinline__ void unlinear_col(const K1Seg& sg, int lin, int& s, i
 // no fence (nobody else reads them before the next inter-CTA barrier).  A full list (LCAP >= top_k entries) keeps its LCAP
 // largest scores, which keeps the selection exact for any input; that path only runs when > 32 scores of ONE thread's
 // ~500 columns pass the lower bound.
+// (all LCAP loads of a scan are issued before the first compare: one L2 round trip per call, not LCAP)
 __device__ __noinline__ float list_min(const uint2* lst) {
+    float v[LCAP];
+#pragma unroll
+    for (int u = 0; u < LCAP; ++u) v[u] = __uint_as_float(__ldcg(&lst[u]).x);
     float m = INFINITY;
-    for (int u = 0; u < LCAP; ++u) m = fminf(m, __uint_as_float(__ldcg(&lst[u]).x));
+#pragma unroll
+    for (int u = 0; u < LCAP; ++u) m = fminf(m, v[u]);
     return m;
 }
 __device__ __noinline__ float list_replace_min(uint2* lst, float sc, int lin) {
+    float vv[LCAP];
+#pragma unroll
+    for (int u = 0; u < LCAP; ++u) vv[u] = __uint_as_float(__ldcg(&lst[u]).x);
     float m1 = INFINITY, m2 = INFINITY; int p1 = 0;
+#pragma unroll
     for (int u = 0; u < LCAP; ++u) {
-        const float v = __uint_as_float(__ldcg(&lst[u]).x);
+        const float v = vv[u];
         if (v < m1) { m2 = m1; m1 = v; p1 = u; } else if (v < m2) { m2 = v; }
     }
     if (sc > m1) {
@@ -1452,7 +1461,13 @@ int k1_launch(const xm_affinity_args_t* a, const K1Maps& maps, const K1Ws& w, in
     p.do_usage = (group == 0) ? 1 : 0;
     p.mode = mode;
     p.qtiles = g.qtiles; p.qpairs = g.qpairs; p.nslice1 = g.nslice1;
-    p.a_stride = a->debug_scores ? 1 : 2;        // the test dump wants every score
+    // Sweep A looks at EVERY key tile.  Sampling every 2nd tile is a valid bound and 9 us cheaper at the config-2 maximum, but on
+    // real videos the best matches of a query sit in a few neighbouring tiles (the same spot of the latest frames); when those
+    // are not sampled the bound is loose, thread lists overflow and sweep B falls off a cliff (measured in the clip: 160 us
+    // instead of 18).  With every tile the bound leaves 31 candidates per query on average (max ~50) instead of 62 (max ~250).
+    // XMEM_K1_A_STRIDE=2 restores the sampled sweep for experiments.
+    static const int a_stride_env = [] { const char* e = getenv("XMEM_K1_A_STRIDE"); const int v = e ? atoi(e) : 1; return v >= 1 && v <= 4 ? v : 1; }();
+    p.a_stride = a->debug_scores ? 1 : a_stride_env;        // the test dump wants every score
     k1_plan_items(g, gr.n_obj, p);
     p.uacc = w.uacc; p.uacc_cols = (int)(w.uacc_cols > 0x7fffffff ? 0x7fffffff : w.uacc_cols);
     p.ctr = w.ctr; p.timeline = w.timeline; p.candA = w.candA; p.tau_lo = w.tau_lo; p.lists = w.lists; p.lcnt = w.lcnt; p.fin = w.fin; p.partial = w.partial;
