@@ -47,3 +47,12 @@ for lo, hi in ((0, 1), (1, 2), (2, 4), (4, 8), (8, 20), (20, 100), (100, 1e9)):
 print('per kernel (warm, inside graphs): total ms | n | avg us')
 for name, (t, c) in sorted(tot.items(), key=lambda kv: -kv[1][0])[:40]:
     print(f'  {t / 1e3:8.2f} | {c:5d} | {t / c:7.1f} | {name[:90]}')
+
+# one ordinary frame in launch order: the kernels between two consecutive k1_fused launches late in the clip
+k1_idx = [i for i, (s_, e_, nm) in enumerate(ks) if 'k1_fused' in nm]
+if len(k1_idx) > 60:
+    a, b = k1_idx[57], k1_idx[58]
+    print(f'--- kernels from one memory read to the next (frame ~58), {b - a} activities, {(ks[b][0] - ks[a][0]):.1f} us:')
+    for s_, e_, nm in ks[a:b]:
+        short = nm.replace('(anonymous namespace)::', '').replace('void ', '')[:70]
+        print(f'   +{s_ - ks[a][0]:8.1f} us  {e_ - s_:7.1f} us  {short}')

@@ -77,3 +77,11 @@ def test_conv1x1_stride2():
 def test_conv_cout_not_multiple_of_64():
     _run(1, 24, 40, [256], 1, 3, 1)
     _run(1, 24, 40, [64], 129, 3, 1)
+
+
+def test_relu_copy_through_the_tma_epilogue():
+    # decoder.up_8_4 out_conv.conv2 (group_modules.py:47-54: g and relu(g) both live on): BN = 128, 3 stages, residual
+    _run(1, 120, 216, [256], 256, 3, 1, residual=True, relu_copy=True, seed=3)
+    # BN = 64 variants: short and long K loops, two objects
+    _run(2, 30, 54, [128], 64, 3, 1, residual=True, relu_copy=True, seed=4)
+    _run(1, 60, 108, [64], 128, 1, 1, relu_copy=True, seed=5)

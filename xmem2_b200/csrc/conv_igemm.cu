@@ -63,6 +63,7 @@ struct alignas(64) ConvMaps {
     CUtensorMap w;
     CUtensorMap o;      // output   [out_stride, Wo, Ho, B]   box [64, TW, TH, 1]   (TMA-store epilogue)
     CUtensorMap r;      // residual [cout, Wo, Ho, B|1]       box [64, TW, TH, 1]
+    CUtensorMap o2;     // second, ReLU'd output (same geometry as o) when relu_copy_tma
 };
 
 struct ConvP {
@@ -84,6 +85,7 @@ struct ConvP {
     int out_stride, out_offset;
     int splits, ksteps_per_split;     // cluster split-K: blockIdx.z (= cluster rank) owns k-steps [z*kps, min((z+1)*kps, ksteps))
     int tma_epilogue;                 // 1: stage the tile in swizzled smem, residual in / output out through TMA
+    int relu_copy_tma;                // 1: the TMA epilogue also writes max(x, 0) to out_relu (splits == 1, >= 3 stages at BN = 128)
 };
 
 template <int BN, int CONV_STAGES>
@@ -271,6 +273,19 @@ conv_igemm_csk_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
                         }
                     }
                 }
+                if (p.relu_copy_tma) {
+                    // second output max(x, 0) (GroupResBlock hands both g and relu(g) on): box k lives in a pipeline stage that
+                    // neither the output nor the residual staging uses (BN = 64: a[1]; BN = 128: a[2], b[2])
+                    uint8_t* rbase = (BN == 64) ? (&sm.a[0][0] + 128 * 128) : (k == 0 ? (&sm.a[0][0] + 2 * 128 * 128) : (&sm.b[0][0] + 2 * BN * 128));
+                    uint8_t* rrow2 = rbase + row * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint4 u;
+                        u.x = pack_half2(fmaxf(v[8 * c], 0.f), fmaxf(v[8 * c + 1], 0.f)); u.y = pack_half2(fmaxf(v[8 * c + 2], 0.f), fmaxf(v[8 * c + 3], 0.f));
+                        u.z = pack_half2(fmaxf(v[8 * c + 4], 0.f), fmaxf(v[8 * c + 5], 0.f)); u.w = pack_half2(fmaxf(v[8 * c + 6], 0.f), fmaxf(v[8 * c + 7], 0.f));
+                        *reinterpret_cast<uint4*>(rrow2 + ((c ^ (row & 7)) << 4)) = u;
+                    }
+                }
                 uint8_t* orow = stage_out + k * 128 * 128 + row * 128;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -289,6 +304,12 @@ conv_igemm_csk_kernel(const __grid_constant__ ConvMaps maps, const ConvP p) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (threadIdx.x == 64) {
                 for (int k = 0; k < nbox; ++k) tma_store_4d(&maps.o, stage_out + k * 128 * 128, p.out_offset + n0 + 64 * k, x0, y0, b);
+                if (p.relu_copy_tma) {
+                    for (int k = 0; k < nbox; ++k) {
+                        const uint8_t* rbase = (BN == 64) ? (&sm.a[0][0] + 128 * 128) : (k == 0 ? (&sm.a[0][0] + 2 * 128 * 128) : (&sm.b[0][0] + 2 * BN * 128));
+                        tma_store_4d(&maps.o2, rbase, p.out_offset + n0 + 64 * k, x0, y0, b);
+                    }
+                }
                 tma_store_commit();
                 tma_store_wait_read();
             }
@@ -500,24 +521,6 @@ extern "C" int xm_conv2d_nhwc(const xm_conv_args_t* a, void* stream_) {
         uint32_t bx[2] = {64, (uint32_t)BN};
         if (xm_make_tmap_f16(&maps.w, a->weight, 2, d, st, bx)) return XM_ERR_CUDA;
     }
-    // TMA epilogue: whole 64-channel boxes, a single plain output (no second ReLU'd copy), 16-byte aligned channel offsets
-    p.tma_epilogue = (a->cout % 64 == 0 && a->out && !a->out_relu && a->out_offset % 8 == 0 && a->out_stride % 8 == 0) ? 1 : 0;
-    {
-        const void* obase = p.tma_epilogue ? a->out : a->src[0].ptr;
-        const uint64_t OC = p.tma_epilogue ? (uint64_t)a->out_stride : (uint64_t)a->src[0].channels;
-        const uint64_t OW = p.tma_epilogue ? (uint64_t)p.Wo : (uint64_t)a->W, OH = p.tma_epilogue ? (uint64_t)p.Ho : (uint64_t)a->H;
-        uint64_t d[4] = {OC, OW, OH, (uint64_t)(p.tma_epilogue ? a->batch : 1)};
-        uint64_t st[3] = {OC * 2, OW * OC * 2, OH * OW * OC * 2};
-        uint32_t bx[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
-        if (xm_make_tmap_f16(&maps.o, obase, 4, d, st, bx)) return XM_ERR_CUDA;
-        if (p.tma_epilogue && a->residual) {
-            uint64_t dr[4] = {(uint64_t)a->cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)(a->residual_broadcast ? 1 : a->batch)};
-            uint64_t sr[3] = {(uint64_t)a->cout * 2, (uint64_t)p.Wo * a->cout * 2, (uint64_t)p.Ho * p.Wo * a->cout * 2};
-            if (xm_make_tmap_f16(&maps.r, a->residual, 4, dr, sr, bx)) return XM_ERR_CUDA;
-        } else {
-            maps.r = maps.o;
-        }
-    }
     // occupancy plan: many CTAs -> 3 stages (2 CTAs/SM overlap prologue/epilogue); few CTAs -> 6 stages (hide L2
     // latency in the k-loop) and split-K over blockIdx.z so that idle SMs share the reduction.
     int cb_total = 0;
@@ -536,6 +539,32 @@ extern "C" int xm_conv2d_nhwc(const xm_conv_args_t* a, void* stream_) {
     p.splits = (ksteps + p.ksteps_per_split - 1) / p.ksteps_per_split;      // no empty split: every CTA issues >= 1 MMA
     int depth = (p.splits > 1) ? 6 : ((p.ksteps_per_split <= 4) ? 2 : ((ctas < 2 * sms) ? 6 : 3));
     if (p.splits == 1 && (f_depth == 2 || f_depth == 3 || f_depth == 6)) depth = f_depth;
+    // TMA epilogue: whole 64-channel boxes, 16-byte aligned channel offsets; a second ReLU'd copy only when a pipeline stage is
+    // left over to stage it in (no split-K partials in the A ring, >= 3 stages at BN = 128)
+    const bool relu_copy_ok = a->out_relu == nullptr || (p.splits == 1 && depth >= (BN == 64 ? 2 : 3));
+    p.tma_epilogue = (a->cout % 64 == 0 && a->out && relu_copy_ok && a->out_offset % 8 == 0 && a->out_stride % 8 == 0) ? 1 : 0;
+    p.relu_copy_tma = (p.tma_epilogue && a->out_relu) ? 1 : 0;
+    {
+        const void* obase = p.tma_epilogue ? a->out : a->src[0].ptr;
+        const uint64_t OC = p.tma_epilogue ? (uint64_t)a->out_stride : (uint64_t)a->src[0].channels;
+        const uint64_t OW = p.tma_epilogue ? (uint64_t)p.Wo : (uint64_t)a->W, OH = p.tma_epilogue ? (uint64_t)p.Ho : (uint64_t)a->H;
+        uint64_t d[4] = {OC, OW, OH, (uint64_t)(p.tma_epilogue ? a->batch : 1)};
+        uint64_t st[3] = {OC * 2, OW * OC * 2, OH * OW * OC * 2};
+        uint32_t bx[4] = {64, (uint32_t)p.tw, (uint32_t)p.th, 1};
+        if (xm_make_tmap_f16(&maps.o, obase, 4, d, st, bx)) return XM_ERR_CUDA;
+        if (p.relu_copy_tma) {
+            if (xm_make_tmap_f16(&maps.o2, a->out_relu, 4, d, st, bx)) return XM_ERR_CUDA;
+        } else {
+            maps.o2 = maps.o;
+        }
+        if (p.tma_epilogue && a->residual) {
+            uint64_t dr[4] = {(uint64_t)a->cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)(a->residual_broadcast ? 1 : a->batch)};
+            uint64_t sr[3] = {(uint64_t)a->cout * 2, (uint64_t)p.Wo * a->cout * 2, (uint64_t)p.Ho * p.Wo * a->cout * 2};
+            if (xm_make_tmap_f16(&maps.r, a->residual, 4, dr, sr, bx)) return XM_ERR_CUDA;
+        } else {
+            maps.r = maps.o;
+        }
+    }
     if (BN == 128) {
         if (depth == 2) return launch_conv<128, 2>(maps, p, a->cout_pad, stream);
         if (depth == 3) return launch_conv<128, 3>(maps, p, a->cout_pad, stream);
