@@ -17,7 +17,7 @@ import torch
 from .. import lib
 from ..model.aggregate import aggregate
 from ..model.network import XMem
-from ..util.tensor_util import pad_divide_by, unpad
+from ..util.tensor_util import pad_amounts, pad_divide_by, unpad
 from .memory_manager import MemoryManager
 
 
@@ -108,18 +108,20 @@ class InferenceCore:
              disable_memory_updates=False, do_not_add_mask_to_memory=False, return_key_and_stuff=False):
         """image 3xHxW (normalised), mask num_objects x H x W or None -> probabilities (num_objects+1) x H x W."""
         self.curr_ti += 1
-        image = self._prepare(image)
+        raw = image
         is_mem_frame, is_deep_update, is_normal_update = self._schedule(mask is not None, end, manually_curated_masks)
         need_segment = (valid_labels is None) or (len(self.all_labels) != len(valid_labels))
 
         if (self.use_cuda_graph and mask is None and need_segment and not end and not disable_memory_updates
-                and not return_key_and_stuff and image.is_cuda and self.memory.get_hidden() is not None):
+                and not return_key_and_stuff and raw.is_cuda and raw.dim() == 3 and self.memory.get_hidden() is not None):
+            # steady-state frames: the unpadded frame is copied straight into the interior of the graph's (zero-bordered) input
+            # buffer -- no F.pad, no intermediate copy
             if is_normal_update and not is_mem_frame:
-                prob = self._graph_step(image, mem_frame=False)
+                prob = self._graph_step(raw, mem_frame=False)
                 if prob is not None:
                     return unpad(prob, self.pad).clone()      # the graph's output buffer is rewritten by the next replay
             elif is_mem_frame and is_deep_update and self.deep_update_sync and not do_not_add_mask_to_memory:
-                prob = self._graph_step(image, mem_frame=True)
+                prob = self._graph_step(raw, mem_frame=True)
                 if prob is not None:
                     # the recorded graph produced key/shrinkage/value/selection and the deep-updated hidden state;
                     # the arena append has a moving offset and stays eager (inference_core.py:136-145)
@@ -129,6 +131,7 @@ class InferenceCore:
                     self.last_deep_update_ti = self.curr_ti
                     return unpad(prob, self.pad).clone()
 
+        image = self._prepare(raw)
         if (self.use_cuda_graph and mask is not None and not need_segment and is_mem_frame and not disable_memory_updates
                 and not return_key_and_stuff and image.is_cuda and mask.shape[0] == len(self.all_labels)
                 and (is_deep_update == self.deep_update_sync)):
@@ -193,7 +196,7 @@ class InferenceCore:
         return res
 
     # ------------------------------------------------------------------ CUDA-graph replay of steady-state frames
-    def _graph_step(self, image, mem_frame):
+    def _graph_step(self, raw, mem_frame):
         """One frame replayed from a recorded CUDA graph.
           mem_frame=False: encode_key -> match_memory -> segment(h_out=True) -> hidden update        (ordinary frame)
           mem_frame=True : encode_key -> match_memory -> segment(h_out=False) -> encode_value(deep)  (memory frame)
@@ -202,7 +205,11 @@ class InferenceCore:
         whenever a memory frame changed them.  Returns None when this frame must run eagerly (first frame with a new
         signature = warm-up of lazily initialised kernel state)."""
         mem = self.memory
-        sig = (tuple(image.shape), mem.layout_signature(), len(self.all_labels), bool(mem_frame))
+        self.pad = pad_amounts(raw, 16)
+        lw, uw, lh, uh = self.pad
+        hr, wr = raw.shape[-2:]
+        shape = (1, raw.shape[0], hr + lh + uh, wr + lw + uw)             # the padded frame the network sees
+        sig = (shape, mem.layout_signature(), len(self.all_labels), bool(mem_frame))
         g = self._graphs.get(sig)
         if g is None:
             cache = _graph_cache(self.network)
@@ -211,7 +218,7 @@ class InferenceCore:
                 if sig not in self._graph_warm:
                     self._graph_warm.add(sig)           # run this frame eagerly, record on the next one
                     return None
-                g = self._capture(image, mem_frame)
+                g = self._capture(self._prepare(raw), mem_frame)
                 if len(cache) >= _GRAPH_CACHE_MAX:
                     cache.pop(next(iter(cache)))
                 cache[sig] = g
@@ -232,9 +239,9 @@ class InferenceCore:
         if hid.data_ptr() != g_hidden.data_ptr():
             g_hidden.copy_(hid)
             mem.set_hidden(g_hidden)
-        g['image'].copy_(image)
-        h, w = image.shape[-2] // 16, image.shape[-1] // 16
-        mem.upload_plan(h * w, image.device)
+        g['image'][0, :, lh:lh + hr, lw:lw + wr].copy_(raw)                 # borders stay zero (F.pad of the recording frame)
+        h, w = shape[-2] // 16, shape[-1] // 16
+        mem.upload_plan(h * w, raw.device)
         g['graph'].replay()
         lib.load().xm_add_launch_count(g['launches'])
         self._g_out = g

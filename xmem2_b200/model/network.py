@@ -159,6 +159,15 @@ class XMem(nn.Module):
                 bn = conv.replace('conv', 'bn') if '.downsample.0' not in conv else conv.replace('downsample.0', 'downsample.1')
             w, b = self._folded(conv, bn)
             put(conv, w, b, cin_pad=320 if conv == 'decoder.hidden_update.g4_conv' else None)
+        # HiddenUpdater (modules.py:52-61): g16_conv(g16) + g8_conv(down(g8)) + g4_conv(down(g4)) = ONE 1x1 conv over the channel
+        # concatenation [512 | 256 | 257 -> 320] (three sources of the implicit GEMM, one fp32 accumulation, summed bias)
+        if not self.disable_hidden and 'decoder.hidden_update.g16_conv.weight' in self._spec:
+            w16, b16 = self._folded('decoder.hidden_update.g16_conv'); w8, b8 = self._folded('decoder.hidden_update.g8_conv')
+            w4, b4 = self._folded('decoder.hidden_update.g4_conv')
+            c16, c8, c4 = w16.shape[1], w8.shape[1], w4.shape[1]
+            wf = torch.zeros((w16.shape[0], c16 + c8 + 320, 1, 1))
+            wf[:, :c16] = w16; wf[:, c16:c16 + c8] = w8; wf[:, c16 + c8:c16 + c8 + c4] = w4
+            put('decoder.hidden_update.g_fused', wf, b16 + b8 + b4)
         # key projection: key | d | e in one GEMM (modules.py:194-211)
         wk, bk = self._folded('key_proj.key_proj'); wd, bd = self._folded('key_proj.d_proj'); we, be = self._folded('key_proj.e_proj')
         put('key_proj', torch.cat([wk, wd, we], 0), torch.cat([bk, bd, be], 0))
@@ -340,14 +349,12 @@ class XMem(nn.Module):
                                   lib.stream_ptr()), 'xm_conv3x3_c1')
         new_hidden = None
         if h_out and self.hidden_dim > 0:
-            a = self._conv('decoder.hidden_update.g16_conv', [(g16, False)])
             g8d = torch.empty((n, h, w, 256), dtype=torch.float16, device=dev)
             lib.check(L.xm_area_down(g8.data_ptr(), None, n, 2 * h, 2 * w, 256, 2, 256, g8d.data_ptr(), lib.stream_ptr()), 'xm_area_down')
-            b = self._conv('decoder.hidden_update.g8_conv', [(g8d, False)], residual=a)
             g4d = torch.empty((n, h, w, 320), dtype=torch.float16, device=dev)
             lib.check(L.xm_area_down(g4.data_ptr(), logits4.data_ptr(), n, 4 * h, 4 * w, 256, 4, 320, g4d.data_ptr(), lib.stream_ptr()),
                       'xm_area_down')
-            c = self._conv('decoder.hidden_update.g4_conv', [(g4d, False)], residual=b)
+            c = self._conv('decoder.hidden_update.g_fused', [(g16, False), (g8d, False), (g4d, False)])
             vals = self._conv('decoder.hidden_update.transform', [(c, False), (h16h, False)])
             new_hidden = self._gru(vals, h32).permute(0, 3, 1, 2).unsqueeze(0)
         H, W = 16 * h, 16 * w

@@ -2,6 +2,15 @@
 import torch.nn.functional as F
 
 
+def pad_amounts(in_img, d):
+    """(left, right, top, bottom) padding that makes H and W multiples of d -- the pad_array of pad_divide_by (util/tensor_util.py:21-35)"""
+    h, w = in_img.shape[-2:]
+    new_h = h if h % d == 0 else h + d - h % d
+    new_w = w if w % d == 0 else w + d - w % d
+    lh, lw = (new_h - h) // 2, (new_w - w) // 2
+    return (int(lw), int(new_w - w - lw), int(lh), int(new_h - h - lh))
+
+
 def pad_divide_by(in_img, d):
     h, w = in_img.shape[-2:]
     new_h = h if h % d == 0 else h + d - h % d
