@@ -1,8 +1,6 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-echo "default:"; python -m xmem2_b200.util.conv_bench "fuser 3x3 512->512" | head -1
-echo "forced 128,2,6:"; XMEM_CONV_FORCE=128,2,6 python -m xmem2_b200.util.conv_bench "fuser 3x3 512->512" | head -1
-echo "l3 1x1 1024->256 default / forced 128,2,6 / forced 64,3,6:"; python -m xmem2_b200.util.conv_bench "l3 1x1 1024->256" | head -1; XMEM_CONV_FORCE=128,2,6 python -m xmem2_b200.util.conv_bench "l3 1x1 1024->256" | head -1; XMEM_CONV_FORCE=64,3,6 python -m xmem2_b200.util.conv_bench "l3 1x1 1024->256" | head -1
-echo "keyproj default / forced 64,2,6:"; python -m xmem2_b200.util.conv_bench "keyproj" | head -1; XMEM_CONV_FORCE=64,2,6 python -m xmem2_b200.util.conv_bench "keyproj" | head -1
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_conv.py tests/test_gpu_network.py tests/test_gpu_clip.py tests/test_gpu_baseline_shapes.py -x -q > gpurun_out/r2o_pytest.txt 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2o_pytest.txt
+python -m xmem2_b200.util.conv_bench > gpurun_out/r2o_conv_table.txt 2>&1; tail -12 gpurun_out/r2o_conv_table.txt
+timeout 300 python tests/profile_gaps.py 100 > gpurun_out/r2o_gaps_pdl.txt 2>&1; head -4 gpurun_out/r2o_gaps_pdl.txt | tail -2

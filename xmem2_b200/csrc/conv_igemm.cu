@@ -512,7 +512,9 @@ extern "C" int xm_conv2d_nhwc(const xm_conv_args_t* a, void* stream_) {
     int cb_all = 0;
     for (int s = 0; s < p.n_src; ++s) cb_all += p.cblocks[s];
     const int ksteps_all = a->ksize * a->ksize * cb_all;
-    if (BN == 128 && ksteps_all <= 128 && p.tiles_x * p.tiles_y * p.batch * (a->cout_pad / 128) * 2 <= sms_) BN = 64;
+    // (short K loops only: with >= 49 k-steps a 128-wide tile split in two over a cluster pulls 1.5x fewer bytes per FLOP through
+    // each SM than 64-wide tiles and the DSMEM reduction is cheap -- 30x54 512->512: 26.1 -> 18.8 us)
+    if (BN == 128 && ksteps_all <= 48 && p.tiles_x * p.tiles_y * p.batch * (a->cout_pad / 128) * 2 <= sms_) BN = 64;
     if (f_bn == 64 || (f_bn == 128 && a->cout_pad % 128 == 0)) BN = f_bn;
     {
         const uint64_t K = (uint64_t)a->ksize * a->ksize * p.cin_total;

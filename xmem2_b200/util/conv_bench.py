@@ -12,7 +12,7 @@ from ..model.packing import pack_conv
 # (name, batch, H, W, [cin...], cout, k, stride, count_per_frame)
 h, w = 30, 54
 SHAPES = [
-    ('stem 1x1 K192',       1, 240, 432, [192], 64, 1, 1, 1),
+    ('stem 7x7 s2 3->64 (fused)', 1, 480, 864, [3], 64, 7, 2, 1),
     ('res2 1x1 64->64',     1, 120, 216, [64], 64, 1, 1, 1),
     ('res2 3x3 64',         1, 120, 216, [64], 64, 3, 1, 3),
     ('res2 1x1 64->256',    1, 120, 216, [64], 256, 1, 1, 4),
@@ -37,11 +37,28 @@ SHAPES = [
     ('up16 3x3 256->256',   1, 60, 108, [256], 256, 3, 1, 1),
     ('up8 3x3 256 @1/4',    1, 120, 216, [256], 256, 3, 1, 3),
     ('pred 3x3 256->1',     1, 120, 216, [256], 1, 3, 1, 1),
-    ('hu 1x1 512->256',     1, h, w, [512], 256, 1, 1, 1),
-    ('hu 1x1 256->256',     1, h, w, [256], 256, 1, 1, 1),
-    ('hu 1x1 320->256',     1, h, w, [320], 256, 1, 1, 1),
+    ('hu 1x1 (512|256|320)->256', 1, h, w, [512, 256, 320], 256, 1, 1, 1),
     ('hu 3x3 320->192',     1, h, w, [256, 64], 192, 3, 1, 1),
 ]
+
+
+def _time(launch, reps, n):
+    """microseconds per launch: n back-to-back launches recorded in a CUDA graph (so the host launch path is not what gets
+    timed), CUDA-event timed over `reps` replays"""
+    for _ in range(5):
+        launch()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(n):
+            launch()
+    graph.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (n * reps)
 
 
 def conv_table(dev='cuda', only=None, reps=10, n=20):
@@ -50,26 +67,24 @@ def conv_table(dev='cuda', only=None, reps=10, n=20):
     for name, B, H, W, cins, cout, k, s, cnt in SHAPES:
         if only and only not in name:
             continue
+        if k == 7:                                   # the fused stem kernel (csrc/stem7x7.cu), not an implicit GEMM launch
+            img = torch.randn(3, H, W, generator=g).to(dev)
+            wgt = (torch.randn(64, 192, generator=g) * 0.08).half().to(dev); bias = torch.zeros(64, device=dev)
+            out = torch.empty(1, H // 2, W // 2, 64, dtype=torch.float16, device=dev)
+            L = lib.load()
+            launch = lambda: lib.check(L.xm_stem7x7(img.data_ptr(), None, 1, H, W, wgt.data_ptr(), bias.data_ptr(), 192, 1, out.data_ptr(),
+                                                     lib.stream_ptr()), 'xm_stem7x7')
+            us = _time(launch, reps, n)
+            fl = 2.0 * (H // 2) * (W // 2) * 64 * 147
+            tot_us += us * cnt; tot_fl += fl * cnt
+            rows.append(dict(layer=name, us=round(us, 2), tflops=round(fl / us / 1e6, 1), per_frame=cnt))
+            continue
         srcs = [((torch.randn(B, H, W, c, generator=g)).half().to(dev), False) for c in cins]
         cin = sum(cins)
         wgt = torch.randn(cout, cin, k, k, generator=g) * (1.0 / (cin * k * k) ** 0.5)
         wp, bp, _ = pack_conv(wgt, torch.zeros(cout), device=dev)
         out = torch.empty(B, H // s, W // s, cout, dtype=torch.float16, device=dev)
-        for _ in range(5):
-            lib.conv2d_nhwc(srcs, wp, bp, cout, ksize=k, stride=s, relu=True, out=out)
-        torch.cuda.synchronize()
-        # record n back-to-back launches in a CUDA graph so the host launch path is not what gets timed
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            for _ in range(n):
-                lib.conv2d_nhwc(srcs, wp, bp, cout, ksize=k, stride=s, relu=True, out=out)
-        graph.replay(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            graph.replay()
-        e1.record(); torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / (n * reps)
+        us = _time(lambda: lib.conv2d_nhwc(srcs, wp, bp, cout, ksize=k, stride=s, relu=True, out=out), reps, n)
         fl = 2.0 * B * (H // s) * (W // s) * cout * cin * k * k
         tot_us += us * cnt; tot_fl += fl * cnt
         rows.append(dict(layer=name, us=round(us, 2), tflops=round(fl / us / 1e6, 1), per_frame=cnt))
