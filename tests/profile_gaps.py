@@ -56,3 +56,14 @@ if len(k1_idx) > 60:
     for s_, e_, nm in ks[a:b]:
         short = nm.replace('(anonymous namespace)::', '').replace('void ', '')[:70]
         print(f'   +{s_ - ks[a][0]:8.1f} us  {e_ - s_:7.1f} us  {short}')
+
+# one MEMORY frame: the window between the memory reads around a value-encoder stem launch
+v_idx = [i for i, (s_, e_, nm) in enumerate(ks) if 'stem7x7_kernel<5>' in nm]
+if len(v_idx) > 8 and len(k1_idx) > 60:
+    vi = v_idx[8]
+    a = max(i for i in k1_idx if i < vi); later = [i for i in k1_idx if i > vi]
+    b = later[0] if later else len(ks) - 1
+    print(f'--- a memory frame: kernels from the memory read before the value encoder to the next read, {b - a} activities, {(ks[b][0] - ks[a][0]):.1f} us:')
+    for s_, e_, nm in ks[a:b]:
+        short = nm.replace('(anonymous namespace)::', '').replace('void ', '')[:70]
+        print(f'   +{s_ - ks[a][0]:8.1f} us  {e_ - s_:7.1f} us  {short}')

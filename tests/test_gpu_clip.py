@@ -134,3 +134,35 @@ def test_two_interleaved_cores_share_one_recorded_graph_without_crosstalk(net):
     mixed = run(0, other=make_other())
     for a, b in zip(alone, mixed):
         assert torch.equal(a, b)
+
+
+def test_sequential_cores_reuse_the_graph_after_empty_cache(net):
+    # a finished video's arenas are recycled, so the next video of the same shape hits the recorded graph; the graph's read
+    # kernels point into the FIRST core's K1 workspace, which the graph entry keeps alive and the new core adopts.  With the
+    # allocator emptied in between, a dangling workspace pointer would give garbage or fault (round-1 advisor finding).
+    import gc
+    dev = 'cuda'
+    H, W = 96, 128
+
+    def run(use_graph):
+        cfg = dict(BASE); cfg['use_cuda_graph'] = use_graph
+        core = InferenceCore(net, cfg)
+        core.set_all_labels([1])
+        f = lambda ti: synth_frame(ti, H, W, structured=True).to(dev)
+        core.put_to_permanent_memory(f(0), synth_mask(0, H, W, 1).to(dev))
+        core.step(f(0), synth_mask(0, H, W, 1).to(dev), [1], do_not_add_mask_to_memory=True)
+        outs = [core.step(f(ti)).clone() for ti in range(1, 9)]
+        sizes = (core.memory.temporary_work_mem.size, core.memory.permanent_work_mem.size)
+        del core
+        return outs, sizes
+
+    eager, sizes_e = run(False)
+    first, sizes_1 = run(True)
+    gc.collect(); torch.cuda.synchronize(); torch.cuda.empty_cache()
+    junk = [torch.full((1 << 22,), float('nan'), device=dev) for _ in range(8)]      # occupy whatever was just freed
+    second, sizes_2 = run(True)
+    del junk
+    assert sizes_e == sizes_1 == sizes_2
+    for a, b, c in zip(eager, first, second):
+        assert torch.isfinite(c).all()
+        assert (a - b).abs().max().item() < 2e-3 and (a - c).abs().max().item() < 2e-3

@@ -17,6 +17,8 @@ properties, `get_v_size`, ...) returns reference-shaped VIEWS of the arenas.
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional
 
 import torch
@@ -32,8 +34,24 @@ def _round_up(x, m):
 
 # Arenas of finished videos are recycled: a serving process handles many clips, and re-using the same device
 # addresses lets InferenceCore re-use its recorded CUDA graphs (their kernels have the arena addresses baked in).
+# The pool is bounded by entries per key AND by total bytes (XMEM_ARENA_POOL_MB, default 4096); `clear_arena_pool()` drops it (call
+# it before torch.cuda.empty_cache() if the memory is wanted back; the recorded graphs of arenas that are gone are simply
+# re-recorded).  The reference-shaped views handed out by `key` / `value` / `shrinkage` / `get_usage` alias the arena: they are
+# valid while the store is alive (a recycled arena is overwritten by the next video) -- clone them to keep them.
 _ARENA_POOL = {}
 _ARENA_POOL_MAX = 8
+_ARENA_POOL_BYTES = [0]
+_ARENA_POOL_LIMIT = int(os.environ.get('XMEM_ARENA_POOL_MB', '4096')) * (1 << 20)
+
+
+def _arena_bytes(arena):
+    return sum(t.numel() * t.element_size() for t in arena)
+
+
+def clear_arena_pool():
+    """drop every pooled arena (their device memory goes back to the caching allocator)"""
+    _ARENA_POOL.clear()
+    _ARENA_POOL_BYTES[0] = 0
 
 
 class KeyValueMemoryStore:
@@ -55,7 +73,9 @@ class KeyValueMemoryStore:
         cap = _round_up(max(cap, 64), 64)
         pooled = _ARENA_POOL.get((str(device), cap, max(n_obj, 1)))
         if pooled:
-            kp, s, e, v, use, life = pooled.pop()        # stale contents are finite and masked by `size`
+            arena = pooled.pop()                          # stale contents are finite and masked by `size`
+            _ARENA_POOL_BYTES[0] -= _arena_bytes(arena)
+            kp, s, e, v, use, life = arena
         else:
             kp = torch.zeros((cap, 2 * CK), dtype=torch.float16, device=device)
             s = torch.ones((cap,), dtype=torch.float32, device=device)
@@ -76,8 +96,11 @@ class KeyValueMemoryStore:
         if self._kp is not None:
             key = (str(self._dev), self._cap, self._v.shape[0])
             lst = _ARENA_POOL.setdefault(key, [])
-            if len(lst) < _ARENA_POOL_MAX:
-                lst.append((self._kp, self._s, self._e, self._v, self._use, self._life))
+            arena = (self._kp, self._s, self._e, self._v, self._use, self._life)
+            nbytes = _arena_bytes(arena)
+            if len(lst) < _ARENA_POOL_MAX and _ARENA_POOL_BYTES[0] + nbytes <= _ARENA_POOL_LIMIT:
+                lst.append(arena)
+                _ARENA_POOL_BYTES[0] += nbytes
             self._kp = None
 
     def __del__(self):
