@@ -17,6 +17,8 @@ Printed JSON (one line, rank 0):
              next frame; every frame's mask is on the host before the clock stops)
   roofline   the fused affinity+readout kernel (K1, one launch) at the config-2 memory size, CUDA-event timed in here;
              `traffic` is the DRAM bytes of one launch from the committed ncu capture, stamped with its git revision
+  roofline_1080p_shape  the same kernel at the config-4 memory size (HW = 8160, 11 frames)
+  conv_roofline  every convolution shape of one 480p frame, graph-timed per shape, summed with its multiplicity
   cpu_baseline  the oracle port (oracle/xmem_oracle.py, plain PyTorch fp32) on this box's host cores, bounded sample;
              its label maps also CHECK this pipeline's output on the same frames (`check`)
   reference_style_gpu  the oracle under CUDA fp16 autocast (cuDNN/cuBLAS, torch.cat memory) = how the reference runs on

@@ -8,18 +8,21 @@
 // ONE persistent kernel per object group (k1_fused), one CTA per SM, all CTAs co-resident; the phases are separated by
 // inter-CTA barriers on global counters:
 //   sweep A   S = Qp.Kp^T tiles (tcgen05, 256 queries x 128 memory columns per key tile: two query tiles share every
-//             key tile, which halves the per-SM TMA ingest), every scan thread keeps 16 branch-free running maxima of
-//             disjoint column subsets ("slot maxima").
+//             key tile, which halves the per-SM TMA ingest), every scan thread keeps 8 branch-free running maxima of
+//             disjoint column subsets ("slot maxima").  Every key tile is swept (a sampled sweep is cheaper but its bound
+//             collapses on real videos, see k1_launch).
 //   merge A   tau_lo[q] = k-th largest slot maximum  (a LOWER bound of the true k-th largest score: the maxima belong
 //             to distinct memory columns).
 //   sweep B   the same S tiles again (bit-identical instruction stream); every score > pred(tau_lo) is appended with its
-//             column index to a per-(slice, query) list (exact top-64 of the slice when more than 64 survive).
+//             column index to a thread-private list (32 entries per (query, slice, tile parity); a full list keeps its 32
+//             largest scores, which keeps the selection exact for any input).
 //   merge B   exact top-k per query on 64-bit keys (score, lowest column first), weights exp(S)/sum exp(S) (no max
-//             subtraction, memory_util.py:48-49), usage atomics, final (column, weight) list per query.
+//             subtraction, memory_util.py:48-49), final (column, weight) list per query.
 //   readout   O[q, c] += P[q, n] V[n, c]  as a dense tcgen05 contraction (the reference's dense v @ affinity):
 //             CTA = 256 queries x 256 value channels x a slice of the memory columns, O in TMEM (2 x 256 columns),
 //             V tiles by TMA, the P tile is zero except for the listed entries, which are scattered into the swizzled
-//             smem operand (and cleared again after use).  No score is recomputed in this phase.
+//             smem operand (and cleared again after use).  No score is recomputed in this phase.  The warps that do not
+//             build P tiles sum the usage (column sums of P, memory_util.py:62-63) in 2^-40 fixed point.
 //   reduce    sum of the column-slice partials -> fp16 CHW / NHWC (or fp32 for the T-sharded mode).
 // Math.  Packed operands Kp[n] = (k_n^2, k_n), Qp[q] = (-e_q, 2 k_q e_q) (fp16, 128 wide):
 //     S'[q,n] = Qp[q] . Kp[n]                                (tcgen05.mma, fp32 accumulate)
