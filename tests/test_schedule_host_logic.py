@@ -27,3 +27,20 @@ def test_schedule_matches_reference_rules():
             core.curr_ti, core.last_mem_ti, core.last_deep_update_ti = curr, last_mem, last_deep
             assert core._schedule(has_mask, end, curated) == _expected(curr, last_mem, last_deep, mem_every, deep_every,
                                                                        has_mask, end, curated)
+
+
+def test_pad_amounts_matches_pad_divide_by():
+    # the steady-state graph path copies the unpadded frame into the interior of a zero-bordered buffer using pad_amounts();
+    # it must describe exactly the padding pad_divide_by (reference util/tensor_util.py:21-35) applies
+    import torch
+    from xmem2_b200.util.tensor_util import pad_amounts, pad_divide_by, unpad
+    for h, w in ((480, 854), (853, 480), (1080, 1920), (96, 128), (17, 33), (16, 16)):
+        x = torch.arange(3 * h * w, dtype=torch.float32).reshape(3, h, w)
+        padded, pads = pad_divide_by(x, 16)
+        assert pads == pad_amounts(x, 16)
+        lw, uw, lh, uh = pads
+        assert padded.shape[-2] % 16 == 0 and padded.shape[-1] % 16 == 0
+        buf = torch.zeros_like(padded)
+        buf[:, lh:lh + h, lw:lw + w].copy_(x)
+        assert torch.equal(buf, padded)
+        assert torch.equal(unpad(padded, pads), x)
