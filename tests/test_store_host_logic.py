@@ -109,3 +109,25 @@ def test_long_term_group_with_fewer_prototypes_stays_right_aligned():
         ostore.add(key.float(), [v0.float(), v1.float()], shr, None, None)
         _same(store, ostore)
     assert store.get_v_size(1) == 42 and store.group_begin(1) == 48 - 42
+
+
+def test_arena_pool_is_bounded_by_bytes_and_can_be_cleared(monkeypatch):
+    # round-1 advisor finding: the pool of recycled arenas must not grow without bound and must be droppable
+    import torch
+    from xmem2_b200.inference import kv_memory_store as K
+    K.clear_arena_pool()
+    dev = torch.device('cpu')
+    s1 = K.KeyValueMemoryStore(count_usage=True)
+    s1._alloc(256, 1, dev)
+    one = K._arena_bytes((s1._kp, s1._s, s1._e, s1._v, s1._use, s1._life))
+    monkeypatch.setattr(K, '_ARENA_POOL_LIMIT', int(one * 1.5))          # room for exactly one pooled arena of this size
+    s2 = K.KeyValueMemoryStore(count_usage=True)
+    s2._alloc(256, 1, dev)
+    s1._release(); s2._release()
+    assert K._ARENA_POOL_BYTES[0] == one and sum(len(v) for v in K._ARENA_POOL.values()) == 1
+    s3 = K.KeyValueMemoryStore(count_usage=True)
+    s3._alloc(256, 1, dev)                                                # takes the pooled arena back
+    assert K._ARENA_POOL_BYTES[0] == 0
+    s3._release()
+    K.clear_arena_pool()
+    assert K._ARENA_POOL_BYTES[0] == 0 and not K._ARENA_POOL
